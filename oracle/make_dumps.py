@@ -1,0 +1,35 @@
+"""Generate the physics dumps used as fixtures (run by `make -C oracle dumps`).
+
+The dumps are produced by the reference's own pumas_physics_create +
+pumas_physics_dump (src/pumas.c:1916, 2167) through oracle/_ref. They are the
+interchange format between the reference and the GPU library:
+both sides load the same bytes. Outputs (gzip, committed):
+    tests/golden/materials.muon.pumas.gz   examples/data/materials.xml, muon
+    tests/golden/ice.tau.pumas.gz          oracle/data/ice.xml, tau
+"""
+import ctypes
+import gzip
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+lib = ctypes.CDLL(os.path.join(HERE, "_ref", "libpumas_oracle.so"))
+lib.oracle_physics_create_and_dump.argtypes = [
+    ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
+
+JOBS = [
+    (0, "examples/materials.xml", "materials.muon.pumas"),
+    (1, "ice/ice.xml", "ice.tau.pumas"),
+]
+
+for particle, mdf, name in JOBS:
+    mdf_path = os.path.join(HERE, "_ref", "data", mdf)
+    raw = os.path.join(HERE, "_ref", "data", name)
+    rc = lib.oracle_physics_create_and_dump(
+        particle, mdf_path.encode(), None, raw.encode())
+    if rc != 0:
+        sys.exit(f"pumas_physics_create failed for {mdf} (rc={rc})")
+    out = os.path.join(HERE, "..", "tests", "golden", name + ".gz")
+    with open(raw, "rb") as f, gzip.GzipFile(out, "wb", mtime=0) as g:
+        g.write(f.read())
+    print(f"{name}: {os.path.getsize(raw)} B -> {os.path.getsize(out)} B gz")
