@@ -1,0 +1,227 @@
+/*
+ * port_driver.cpp -- CPU debugging build of the single-source transport core.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/oracle_driver.c for the rules). This
+ * compiles the very headers the CUDA kernels are made of (pumas_b200/csrc/
+ * pb_*.h) with g++ so that the restated algorithm can be checked against the
+ * real reference (oracle/_ref) on a machine without a GPU, track by track and
+ * function by function. It is NOT independent of the product (same source), so
+ * it is not evidence of parity by itself: the evidence is `port == reference`
+ * here (tests/test_port_vs_reference.py) and `GPU == reference` on the GPU box
+ * (tests/test_gpu_parity.py).
+ * Each restated function cites the reference lines it follows, in the headers.
+ */
+#include <pthread.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "pb_dump.hpp"
+#include "pb_transport.h"
+#include "philox.h"
+#include "pumas_b200.h"
+
+namespace {
+
+struct PhiloxRng {
+        pb_philox g;
+        double uniform() { return pb_philox_uniform(&g); }
+};
+
+pb::Settings settings_from(const struct pumas_context * c)
+{
+        pb::Settings s;
+        s.energy_loss = (int)c->mode.energy_loss;
+        s.decay = (int)c->mode.decay;
+        s.direction = (int)c->mode.direction;
+        s.scattering = (int)c->mode.scattering;
+        s.event = (int)c->event;
+        s.limit_energy = c->limit.energy;
+        s.limit_distance = c->limit.distance;
+        s.limit_grammage = c->limit.grammage;
+        s.limit_time = c->limit.time;
+        s.accuracy = c->accuracy;
+        return s;
+}
+
+struct Job {
+        const pb::HostPhysics * hp;
+        pb::Settings cfg;
+        const pumas_b200_geometry * geo;
+        uint64_t seed, offset;
+        long begin, end;
+        pb::State * states;
+        int * events;
+        int * media;
+        unsigned int * n_random;
+        unsigned int * n_steps;
+        int rc;
+};
+
+void * worker(void * arg)
+{
+        Job * job = static_cast<Job *>(arg);
+        const pb::Physics & p = job->hp->view;
+        for (long i = job->begin; i < job->end; i++) {
+                PhiloxRng rng;
+                pb_philox_init(&rng.g, job->seed, job->offset + (uint64_t)i);
+                unsigned int steps = 0;
+                const pb::Outcome out = pb::transport_track(
+                    p, job->cfg, *job->geo, rng, job->states[i], &steps);
+                if ((out.rc != 0) && (job->rc == 0)) job->rc = out.rc;
+                if (job->events) job->events[i] = out.event;
+                if (job->media) {
+                        job->media[2 * i] = out.medium[0];
+                        job->media[2 * i + 1] = out.medium[1];
+                }
+                if (job->n_random) job->n_random[i] = rng.g.count;
+                if (job->n_steps) job->n_steps[i] = steps;
+        }
+        return NULL;
+}
+
+} /* namespace */
+
+extern "C" {
+
+void * port_physics_load(const char * path)
+{
+        FILE * f = fopen(path, "rb");
+        if (f == NULL) return NULL;
+        pb::HostPhysics * hp = new pb::HostPhysics;
+        std::string err;
+        const int rc = pb::load_physics_stream(f, *hp, err);
+        fclose(f);
+        if (rc != 0) {
+                fprintf(stderr, "port_physics_load: %s\n", err.c_str());
+                delete hp;
+                return NULL;
+        }
+        return hp;
+}
+
+void port_physics_destroy(void * physics)
+{
+        delete static_cast<pb::HostPhysics *>(physics);
+}
+
+int port_transport_n(const void * physics, const struct pumas_context * settings,
+    const struct pumas_b200_geometry * geometry, uint64_t seed, uint64_t offset,
+    long n, struct pumas_state * states, int * events, int * media,
+    unsigned int * n_random, unsigned int * n_steps, int n_threads)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        const pb::Settings cfg = settings_from(settings);
+        const int rc0 = pb::settings_check(hp->view, cfg);
+        if (rc0 != 0) return rc0;
+        if (n_threads < 1) n_threads = 1;
+        if ((long)n_threads > n) n_threads = (n > 0) ? (int)n : 1;
+        std::vector<Job> jobs(n_threads);
+        std::vector<pthread_t> threads(n_threads);
+        for (int t = 0; t < n_threads; t++) {
+                Job & j = jobs[t];
+                j.hp = hp;
+                j.cfg = cfg;
+                j.geo = geometry;
+                j.seed = seed;
+                j.offset = offset;
+                j.begin = n * t / n_threads;
+                j.end = n * (t + 1) / n_threads;
+                j.states = reinterpret_cast<pb::State *>(states);
+                j.events = events;
+                j.media = media;
+                j.n_random = n_random;
+                j.n_steps = n_steps;
+                j.rc = 0;
+                if (n_threads == 1)
+                        worker(&j);
+                else
+                        pthread_create(&threads[t], NULL, &worker, &j);
+        }
+        int rc = 0;
+        for (int t = 0; t < n_threads; t++) {
+                if (n_threads > 1) pthread_join(threads[t], NULL);
+                if ((rc == 0) && (jobs[t].rc != 0)) rc = jobs[t].rc;
+        }
+        return rc;
+}
+
+/* Function level hooks, mirroring oracle_driver.c. */
+double port_dcs_evaluate(
+    const void * physics, int process, int element, double K, double q)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        return pb::dcs_evaluate(hp->view, process, element, K, q);
+}
+
+double port_dcs_model(
+    const void * physics, int process, int element, double K, double q)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        return pb::dcs_model(
+            hp->view, process, hp->view.element[element], K, q);
+}
+
+double port_coulomb_ehs_length(const void * physics, int material, double K)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        return pb::coulomb_ehs_length(hp->view, material, K);
+}
+
+void port_table_get_msc(const void * physics, int scheme, int material,
+    double K, double * mu0, double * invlb1)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        pb::table_get_msc(hp->view, scheme, material, K, mu0, invlb1);
+}
+
+int port_coulomb_cs_hard(const void * physics, int material, int scheme,
+    double kinetic, double * cs_hard)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        const pb::Physics & p = hp->view;
+        double mu0 = 0., invlb1 = 0.;
+        pb::table_get_msc(p, scheme, material, kinetic, &mu0, &invlb1);
+        const int n = p.elements_in[material];
+        for (int i = 0; i < n; i++)
+                cs_hard[i] = pb::coulomb_cs_hard(
+                    p, p.comp_offset[material] + i, kinetic, mu0);
+        return n;
+}
+
+/* Raw table access, same names as oracle_table(). */
+const double * port_table(const void * physics, const char * name, long * length)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        const pb::Physics & p = hp->view;
+        const long ne = p.n_energies, nm = p.n_materials;
+        const std::string s(name);
+#define T(tag, ptr, len)                                                       \
+        if (s == tag) {                                                        \
+                *length = (len);                                               \
+                return (ptr);                                                  \
+        }
+        T("K", p.K, ne)
+        T("K_dX", p.K_dX, pb::N_SCHEMES * nm * ne)
+        T("X", p.X, pb::N_SCHEMES * nm * ne)
+        T("X_dK", p.X_dK, pb::N_SCHEMES * nm * ne)
+        T("T", p.T, pb::N_SCHEMES * nm * ne)
+        T("dE", p.dE, pb::N_SCHEMES * nm * ne)
+        T("Omega", p.Omega, nm * ne)
+        T("CS", p.CS, nm * ne)
+        T("NI_in", p.NI_in, nm * ne)
+        T("NI_el", p.NI_el, pb::N_SCHEMES * nm * ne)
+        T("Mu0", p.Mu0, nm * ne)
+        T("Lb", p.Lb, nm * ne)
+        T("Ms1", p.Ms1, (pb::N_SCHEMES + 1) * nm * ne)
+        T("Kt", p.Kt, nm)
+        T("a_max", p.a_max, nm)
+        T("b_max", p.b_max, pb::N_SCHEMES * nm)
+#undef T
+        *length = 0;
+        return NULL;
+}
+
+} /* extern "C" */

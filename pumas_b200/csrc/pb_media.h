@@ -1,0 +1,99 @@
+/*
+ * pb_media.h -- built-in media: the device side replacement of the user
+ * `pumas_medium_cb` (pumas.h:509) and `pumas_locals_cb` (pumas.h:348).
+ *
+ * Media are identified by their layer index (-1 = outside, the reference's
+ * NULL medium). Semantics follow the two example geometries of the reference:
+ * examples/pumas/straight.c:61-74 (uniform) and examples/pumas/geometry.c:64-163
+ * (horizontal layers with constant or exponential density and a uniform
+ * magnetic field). oracle/oracle_driver.c implements the same descriptor with
+ * host callbacks for the CPU oracle.
+ */
+#ifndef PB_MEDIA_H
+#define PB_MEDIA_H
+
+#include "pb_physics.h"
+#include "pumas_b200_geometry.h"
+
+namespace pb {
+
+typedef struct pumas_b200_geometry Geometry;
+
+/* struct medium_locals, pumas.c:398-405 */
+struct Locals {
+        double density;
+        double magnet[3];
+        int magnetized;
+};
+
+/* The medium callback. `want_medium` / `want_step` mirror the NULL-ness of the
+ * two out pointers of pumas_medium_cb. Returns the step type. */
+PB_FN int medium_locate(const Geometry & g, int direction, const State & state,
+    bool want_medium, int * medium, bool want_step, double * step_ptr)
+{
+        if (g.kind == PUMAS_B200_GEOMETRY_UNIFORM) {
+                if (want_medium) *medium = 0;
+                if (want_step) *step_ptr = 0.;
+                return g.step_type;
+        }
+        if (!want_medium && !want_step) return g.step_type;
+
+        const double z = state.position[2];
+        const double sgn = (direction == MODE_FORWARD) ? 1 : -1;
+        const double uz = state.direction[2] * sgn;
+        double step = g.step_default;
+        const int n = g.n_layers;
+        if ((z < g.z[0]) || !(z < g.z[n])) {
+                if (want_medium) *medium = -1;
+                step = -1.;
+        } else {
+                int i = 0;
+                while ((i < n - 1) && !(z < g.z[i + 1])) i++;
+                if (want_medium) *medium = i;
+                if (uz > (double)FLT_EPSILON)
+                        step = (g.z[i + 1] - z) / uz;
+                else if (uz < -(double)FLT_EPSILON)
+                        step = (g.z[i] - z) / uz;
+        }
+        if (want_step) {
+                if (step > 0) step += g.step_epsilon;
+                *step_ptr = step;
+        }
+        return g.step_type;
+}
+
+/* transport_set_locals, pumas.c:5528-5552. Returns the proposed locals step
+ * times the accuracy (<= 0: uniform). */
+PB_FN double set_locals(const Physics & p, const Geometry & g, double accuracy,
+    int medium, const State & state, Locals * locals)
+{
+        const struct pumas_b200_layer & l = g.layer[medium];
+        if (!l.has_locals) {
+                locals->density = p.material_density[l.material];
+                locals->magnet[0] = locals->magnet[1] = locals->magnet[2] = 0.;
+                locals->magnetized = 0;
+                return 0;
+        }
+        double step_max;
+        locals->magnet[0] = l.magnet[0];
+        locals->magnet[1] = l.magnet[1];
+        locals->magnet[2] = l.magnet[2];
+        if (l.density_model == PUMAS_B200_DENSITY_EXPONENTIAL) {
+                locals->density = l.density * exp(-state.position[2] / l.scale);
+                const double uz = fabs(state.direction[2]);
+                step_max = l.scale / ((uz <= l.eps) ? l.eps : uz);
+        } else {
+                locals->density = l.density;
+                step_max = 0.;
+        }
+        if (locals->density <= 0)
+                locals->density = p.material_density[l.material];
+        const double * b = locals->magnet;
+        locals->magnetized =
+            ((b[0] != 0.) || (b[1] != 0.) || (b[2] != 0.)) ? 1 : 0;
+        return step_max * accuracy;
+}
+
+} /* namespace pb */
+
+#endif

@@ -1,0 +1,1428 @@
+/*
+ * pb_transport.h -- the per-track transport engine.
+ *
+ * Restates, one track per call (one GPU thread per track):
+ *   pumas_context_transport      src/pumas.c:3114-3251   [a4]
+ *   transport_with_csda          src/pumas.c:4777-4949   [a5]
+ *   transport_with_stepping      src/pumas.c:5194-5514   [a6]
+ *   transport_limit              src/pumas.c:5569-5696   [a7]
+ *   transport_do_del / do_ehs    src/pumas.c:5706-5885   [a14, a15]
+ *   step_transport               src/pumas.c:6296-6925   [a8]
+ *   step_fluctuate / step_randn  src/pumas.c:6943-7029   [a9]
+ *   step_rotate_direction        src/pumas.c:7042-7095   [a10]
+ * The hidden per-context stepping state of the reference
+ * (struct simulation_context, pumas.c:426-477) lives in `Track`, private to the
+ * thread; the recorder hooks are out of scope and the
+ * magnetised closed-form CSDA (transport_csda_deflect, pumas.c:4968) falls
+ * back to stepping.
+ *
+ * The number and order of the uniform variates drawn from `Rng` is part of the
+ * contract with the oracle.
+ */
+#ifndef PB_TRANSPORT_H
+#define PB_TRANSPORT_H
+
+#include "pb_coulomb.h"
+#include "pb_del.h"
+#include "pb_media.h"
+#include "pb_polar.h"
+
+namespace pb {
+
+constexpr int MAX_COMPONENTS = 8; /* elements per material handled by do_ehs */
+
+/* Working precision of the Coulomb pole reduction (see pb_coulomb.h). */
+#if defined(__CUDA_ARCH__) || defined(PB_FORCE_DD)
+typedef dd CoulombReal;
+#else
+typedef long double CoulombReal;
+#endif
+
+/* Hidden stepping state, pumas.c:426-477. */
+struct Track {
+        double lifetime;
+        int step_first;
+        int step_event;
+        int step_foreseen;
+        double step_X_limit;
+        double step_invlb1;
+        int randn_done;
+        double randn_next;
+        int error;           /* enum pumas_return raised inside the stepping */
+        unsigned int n_steps; /* diagnostics: calls of step_transport */
+};
+
+/* pumas.c:7016-7029 */
+template <class Rng> PB_FN double step_randn(Track & trk, Rng & rng)
+{
+        trk.randn_done = !trk.randn_done;
+        if (!trk.randn_done) return trk.randn_next;
+
+        const double r = sqrt(-2. * log(rng.uniform()));
+        const double phi = 2. * PI * rng.uniform();
+        const double c = cos(phi);
+        const double s = sin(phi);
+        trk.randn_next = r * c;
+        return r * s;
+}
+
+/* pumas.c:7042-7095 */
+template <class Rng>
+PB_FN void step_rotate_direction(Rng & rng, State & state, double mu)
+{
+        double * const direction = state.direction;
+
+        const double cos_theta = 1 - 2 * mu;
+        const double stsq = 4 * mu * (1. - mu);
+        if (stsq <= 0.) return;
+        const double st = sqrt(stsq);
+
+        double u0x = 0., u0y = 0., u0z = 0.;
+        const double a0 = fabs(direction[0]);
+        const double a1 = fabs(direction[1]);
+        const double a2 = fabs(direction[2]);
+        if (a0 > a1) {
+                if (a0 > a2) {
+                        const double nrm = 1. /
+                            sqrt(direction[0] * direction[0] +
+                                direction[2] * direction[2]);
+                        u0x = -direction[2] * nrm, u0z = direction[0] * nrm;
+                } else {
+                        const double nrm = 1. /
+                            sqrt(direction[1] * direction[1] +
+                                direction[2] * direction[2]);
+                        u0y = direction[2] * nrm, u0z = -direction[1] * nrm;
+                }
+        } else {
+                if (a1 > a2) {
+                        const double nrm = 1. /
+                            sqrt(direction[0] * direction[0] +
+                                direction[1] * direction[1]);
+                        u0x = direction[1] * nrm, u0y = -direction[0] * nrm;
+                } else {
+                        const double nrm = 1. /
+                            sqrt(direction[1] * direction[1] +
+                                direction[2] * direction[2]);
+                        u0y = direction[2] * nrm, u0z = -direction[1] * nrm;
+                }
+        }
+        const double u1x = u0y * direction[2] - u0z * direction[1];
+        const double u1y = u0z * direction[0] - u0x * direction[2];
+        const double u1z = u0x * direction[1] - u0y * direction[0];
+
+        const double phi = PI * (1. - 2. * rng.uniform());
+        const double cp = cos(phi);
+        const double sp = sin(phi);
+        direction[0] = cos_theta * direction[0] + st * (cp * u0x + sp * u1x);
+        direction[1] = cos_theta * direction[1] + st * (cp * u0y + sp * u1y);
+        direction[2] = cos_theta * direction[2] + st * (cp * u0z + sp * u1z);
+}
+
+/* PENELOPE style straggling of the continuous loss. pumas.c:6943-7005. */
+template <class Rng>
+PB_FN void step_fluctuate(const Physics & p, const Settings & cfg, Track & trk,
+    Rng & rng, const State & state, int material, double Xtot, double dX,
+    double * kf, double * ratio)
+{
+        const int scheme = cfg.energy_loss;
+        const double sgn = (cfg.direction == MODE_FORWARD) ? 1. : -1.;
+        double k1, r = 0.;
+        k1 = cel_kinetic_energy(p, scheme, material, Xtot - sgn * dX);
+        const double dk0 = fabs(state.energy - k1);
+        if ((k1 > 0.) && (dk0 > 0.)) {
+                const double Omega0 = cel_straggling(p, material, state.energy);
+                const double Omega1 = cel_straggling(p, material, k1);
+                double dk12 = 0.5 * dX * (Omega0 + Omega1);
+                const double tmp = dX / Xtot;
+                if (tmp > 5E-02) {
+                        const double de1 =
+                            cel_energy_loss(p, scheme, material, k1);
+                        const double de0 =
+                            cel_energy_loss(p, scheme, material, state.energy);
+                        dk12 *= 1. + sgn * dX / dk0 * (de1 - de0);
+                }
+                const double dk1 = sqrt(dk12);
+                if (dk0 >= 3. * dk1) {
+                        double u;
+                        do
+                                u = step_randn(trk, rng);
+                        while (fabs(u) > 3.);
+                        u /= 1.015387;
+                        k1 += u * dk1;
+                } else if (dk0 >= 1.7320508 * dk1) {
+                        const double u = 1.7320508 * (1. - 2. * rng.uniform());
+                        k1 += u * dk1;
+                } else {
+                        const double dk32 = 3. * dk12;
+                        const double dk02 = dk0 * dk0;
+                        const double a =
+                            1. - (dk32 - dk02) / (dk32 + 3. * dk02);
+                        if (rng.uniform() <= a) {
+                                const double b = 0.5 * (dk32 + 3. * dk02) / dk0;
+                                const double u = rng.uniform();
+                                k1 = state.energy - sgn * b * u;
+                                if (k1 < 0.) k1 = 0.;
+                        } else {
+                                k1 = state.energy;
+                        }
+                }
+                r = fabs(state.energy - k1) / dk0;
+        }
+        if (r == 0.) r = 1.;
+        *kf = k1;
+        *ratio = r;
+}
+
+/* pumas.c:5569-5696 */
+template <class Rng>
+PB_FN void transport_limit(const Physics & p, const Settings & cfg, Track & trk,
+    Rng & rng, const State & state, int material, double Xi, double Xf,
+    double * grammage_max)
+{
+        trk.step_event = trk.step_foreseen = EVENT_NONE;
+
+        if (state.weight <= 0.) {
+                trk.step_event = EVENT_WEIGHT;
+                return;
+        }
+
+        if (cfg.direction == MODE_FORWARD) {
+                const double kinetic_min =
+                    (cfg.event & EVENT_LIMIT_ENERGY) ? cfg.limit_energy : 0.;
+                if (state.energy <= kinetic_min) {
+                        trk.step_event = EVENT_LIMIT_ENERGY;
+                        return;
+                }
+        } else if ((cfg.event & EVENT_LIMIT_ENERGY) &&
+            (state.energy >= cfg.limit_energy)) {
+                trk.step_event = EVENT_LIMIT_ENERGY;
+                return;
+        }
+
+        if (cfg.event & EVENT_LIMIT_GRAMMAGE) {
+                *grammage_max = cfg.limit_grammage;
+                trk.step_foreseen = EVENT_LIMIT_GRAMMAGE;
+        } else {
+                *grammage_max = 0.;
+        }
+
+        const int scheme = cfg.energy_loss;
+        if (scheme == MODE_DISABLED) {
+                if (cfg.scattering == MODE_MIXED) {
+                        const double X = Xi -
+                            coulomb_ehs_length(p, material, state.energy) *
+                                log(rng.uniform());
+                        if ((*grammage_max == 0.) || (X < *grammage_max)) {
+                                *grammage_max = X;
+                                trk.step_foreseen = EVENT_VERTEX_COULOMB;
+                                return;
+                        }
+                }
+                return;
+        }
+
+        const double sgn = (cfg.direction == MODE_FORWARD) ? 1. : -1.;
+        int foreseen = EVENT_NONE;
+        double kinetic_limit = 0.;
+        if (scheme == MODE_MIXED) {
+                for (int i = 0; i < 1000; i++) {
+                        const double zeta = rng.uniform();
+                        if ((zeta <= 0.) || (zeta >= 1.)) continue;
+
+                        const double nI =
+                            del_interaction_length(p, material, state.energy) +
+                            sgn * log(zeta);
+                        if (nI <= 0.) break;
+
+                        const double k = del_kinetic_from_interaction_length(
+                            p, material, nI);
+
+                        if (cfg.direction == MODE_FORWARD) {
+                                if (k >= state.energy) continue;
+                        } else {
+                                if (k <= state.energy) continue;
+                        }
+
+                        if ((cfg.direction == MODE_BACKWARD) ||
+                            (k > p.Kt[material])) {
+                                kinetic_limit = k;
+                                foreseen = EVENT_VERTEX_DEL;
+                        }
+                        break;
+                }
+        }
+
+        if ((scheme < MODE_STRAGGLED) && (cfg.scattering == MODE_MIXED)) {
+                const double nI =
+                    ehs_interaction_length(p, scheme, material, state.energy) +
+                    sgn * log(rng.uniform());
+                if (nI > 0.) {
+                        const double k = ehs_kinetic_from_interaction_length(
+                            p, scheme, material, nI);
+                        if ((kinetic_limit <= 0.) ||
+                            ((cfg.direction == MODE_FORWARD) &&
+                                (k > kinetic_limit)) ||
+                            ((cfg.direction == MODE_BACKWARD) &&
+                                (k < kinetic_limit))) {
+                                kinetic_limit = k;
+                                foreseen = EVENT_VERTEX_COULOMB;
+                        }
+                }
+        }
+
+        if (foreseen == EVENT_NONE) return;
+
+        const double X = Xi +
+            sgn * (Xf - cel_grammage(p, scheme, material, kinetic_limit));
+        if ((*grammage_max <= 0) || (X < *grammage_max)) {
+                *grammage_max = X;
+                trk.step_foreseen = foreseen;
+        }
+}
+
+/* pumas.c:5706-5757 */
+template <class Rng>
+PB_FN void transport_do_del(const Physics & p, const Settings & cfg,
+    Track & trk, Rng & rng, State & state, int material)
+{
+        double ki, kf;
+        int process = -1;
+        int element = 0;
+        bool polar;
+        if (cfg.direction == MODE_FORWARD) {
+                ki = state.energy;
+                polar = del_randomise_forward(
+                    p, cfg, rng, state, material, &process, &element);
+                kf = state.energy;
+        } else {
+                kf = state.energy;
+                polar = del_randomise_reverse(
+                    p, cfg, rng, state, material, &process, &element);
+                ki = state.energy;
+        }
+
+        if (process < 0) {
+                if (state.weight > 0)
+                        trk.step_event = EVENT_NONE;
+                else
+                        trk.step_event = EVENT_WEIGHT;
+        } else {
+                trk.step_event = (process == 0) ?
+                    EVENT_VERTEX_BREMSSTRAHLUNG :
+                    (process == 1) ?
+                    EVENT_VERTEX_PAIR_CREATION :
+                    (process == 2) ?
+                    EVENT_VERTEX_PHOTONUCLEAR :
+                    (process == 3) ? EVENT_VERTEX_DELTA_RAY : EVENT_VERTEX;
+        }
+
+        if ((cfg.scattering == MODE_MIXED) && polar) {
+                if (kf > ki) {
+                        const double tmp = kf;
+                        kf = ki;
+                        ki = tmp;
+                }
+                const double mu =
+                    polar_sample(p, rng, process, p.element[element], ki, kf);
+                step_rotate_direction(rng, state, mu);
+        }
+}
+
+/* Restricted (hard) cross-section of one component, pumas.c:5786-5813. */
+PB_NOINLINE double coulomb_cs_hard(const Physics & p, int component,
+    double kinetic, double mu0)
+{
+        const Element & el = p.element[p.comp_element[component]];
+        CoulombData data;
+        double kinetic0;
+        coulomb_data_set(p, el, kinetic, &data, &kinetic0);
+        CoulombPoles<CoulombReal> poles;
+        coulomb_pole_reduction<CoulombReal>(
+            data.n_parameters, data.amplitude, data.screening, &poles);
+        const double normalisation = p.comp_fraction[component] /
+            coulomb_normalisation(el.Z, el.A, p.mass, kinetic, kinetic0);
+        return normalisation *
+            coulomb_restricted_cs<CoulombReal>(
+                mu0, data.fspin, data.n_parameters, data.screening, poles);
+}
+
+/* pumas.c:5768-5885 */
+template <class Rng>
+PB_FN void transport_do_ehs(const Physics & p, const Settings & cfg, Rng & rng,
+    State & state, int material)
+{
+        const double kinetic = state.energy;
+
+        double mu0 = 0., invlb1 = 0.;
+        table_get_msc(p, cfg.energy_loss, material, kinetic, &mu0, &invlb1);
+
+        /* Randomise the hard scatterer element. For a single element material
+         * the outcome is forced, whatever the cross-section; the variate is
+         * still drawn (pumas.c:5816). */
+        const int n_el = p.elements_in[material];
+        const int ic0 = p.comp_offset[material];
+        int ihard = n_el - 1;
+        if (n_el == 1) {
+                (void)rng.uniform();
+                ihard = 0;
+        } else {
+                double cs_hard[MAX_COMPONENTS];
+                double cs_tot = 0.;
+                int i;
+                for (i = 0; i < n_el; i++) {
+                        cs_hard[i] = coulomb_cs_hard(p, ic0 + i, kinetic, mu0);
+                        cs_tot += cs_hard[i];
+                }
+                const double cc0 = rng.uniform() * cs_tot;
+                double cs = 0.;
+                for (i = 0; i < n_el; i++) {
+                        cs += cs_hard[i];
+                        if (cs >= cc0) {
+                                ihard = i;
+                                break;
+                        }
+                }
+        }
+
+        /* Rejection sampling of the angular parameter under a Wentzel DCS. */
+        CoulombData data;
+        double kinetic0;
+        coulomb_data_set(
+            p, p.element[p.comp_element[ic0 + ihard]], kinetic, &data, &kinetic0);
+        const int n = data.n_parameters - 1;
+        double A = data.screening[0];
+        int i;
+        for (i = 1; i < n; i++) {
+                const double Ai = data.screening[i];
+                if (Ai < A) A = Ai;
+        }
+        double mu1;
+        for (;;) {
+                const double zeta = rng.uniform();
+                const double tmp = 1. + A - zeta * (1 - mu0);
+                if (tmp <= 0.) continue;
+                mu1 = (A + mu0) * (A + 1.) / tmp - A;
+                if (mu1 < mu0)
+                        mu1 = mu0;
+                else if (mu1 > 1.)
+                        mu1 = 1;
+
+                double ratio = 0.;
+                for (i = 0; i < n; i++) {
+                        ratio += data.amplitude[i] * (A + mu1) /
+                            (data.screening[i] + mu1);
+                }
+                ratio *= coulomb_nuclear_form_factor(mu1, data.screening[n]);
+                ratio *= ratio * (1. - data.fspin * mu1);
+
+                if (rng.uniform() <= ratio) break;
+        }
+
+        /* CM to laboratory frame. */
+        const double gamma = data.fCM[0];
+        const double tau = data.fCM[1];
+        double mu;
+        if (mu1 > 1E-06) {
+                const double a = gamma * (tau + 1. - 2. * mu1);
+                const double ct_h = a / sqrt(4. * mu1 * (1. - mu1) + a * a);
+                mu = 0.5 * (1. - ct_h);
+        } else {
+                const double d = gamma * (1. + tau);
+                mu = mu1 / (d * d);
+        }
+        step_rotate_direction(rng, state, mu);
+}
+
+/* One Monte Carlo step in a single medium. pumas.c:6296-6925. Returns false
+ * on error (trk.error set). */
+template <class Rng>
+PB_FN bool step_transport(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Track & trk, Rng & rng, State & state, int straight,
+    int medium, Locals & locals, double grammage_max, double step_max_medium,
+    int step_max_type, double * step_max_locals, int * out_medium)
+{
+        trk.n_steps++;
+        const int scheme = cfg.energy_loss;
+        double * const direction = state.direction;
+        double * const position = state.position;
+        const int material = geo.layer[medium].material;
+        const double density = locals.density;
+        const double density_i = 1. / density;
+        const double momentum = sqrt(state.energy * (state.energy + 2. * p.mass));
+
+        const int tmp_scheme = (scheme == MODE_DISABLED) ? MODE_CSDA : scheme;
+        const double Xtot = cel_grammage(p, tmp_scheme, material, state.energy);
+
+        /* Local step length. */
+        double step_loc, rLarmor0 = 0., uT0[3] = { 0., 0., 0. };
+        double invlb1 = 0.;
+        if (!straight) {
+                double r = cfg.accuracy;
+                const double k_threshold = 1E+09;
+                if ((scheme == MODE_STRAGGLED) && (state.energy > k_threshold)) {
+                        double f = k_threshold / state.energy;
+                        if (f < 0.1) f = 0.1;
+                        r *= f;
+                }
+                step_loc = r * density_i * Xtot;
+
+                if (cfg.scattering == MODE_MIXED) {
+                        if (trk.step_first != 0) {
+                                double mu0;
+                                table_get_msc(p, cfg.energy_loss, material,
+                                    state.energy, &mu0, &invlb1);
+                                invlb1 *= density;
+                        } else
+                                invlb1 = trk.step_invlb1;
+                        const double stepT = cfg.accuracy / invlb1;
+                        if (stepT < step_loc) step_loc = stepT;
+                }
+
+                if (locals.magnetized == 0) {
+                        rLarmor0 = 0.;
+                } else {
+                        const double * const B = locals.magnet;
+                        uT0[0] = direction[1] * B[2] - direction[2] * B[1];
+                        uT0[1] = direction[2] * B[0] - direction[0] * B[2];
+                        uT0[2] = direction[0] * B[1] - direction[1] * B[0];
+                        const double BT = sqrt(
+                            uT0[0] * uT0[0] + uT0[1] * uT0[1] + uT0[2] * uT0[2]);
+                        if (BT == 0.) {
+                                rLarmor0 = 0.;
+                        } else {
+                                rLarmor0 = momentum / (BT * LARMOR_FACTOR);
+                                const double pinv = 1. / momentum;
+                                uT0[0] *= pinv;
+                                uT0[1] *= pinv;
+                                uT0[2] *= pinv;
+                        }
+                }
+
+                if (rLarmor0 > 0.) {
+                        const double stepM = cfg.accuracy * rLarmor0;
+                        if (stepM < step_loc) step_loc = stepM;
+                }
+        } else {
+                if (grammage_max <= 0.)
+                        step_loc = 1E+09 * density_i;
+                else
+                        step_loc = grammage_max * density_i;
+        }
+
+        trk.step_first = 0;
+
+        if (step_loc < STEP_MIN) step_loc = STEP_MIN;
+        double step = (step_max_medium <= 0) ?
+            step_loc :
+            (step_max_medium < step_loc ? step_max_medium : step_loc);
+        if ((*step_max_locals > 0.) && (step > *step_max_locals))
+                step = *step_max_locals;
+
+        *out_medium = medium;
+        int event = EVENT_NONE;
+        if (cfg.event & EVENT_LIMIT_DISTANCE) {
+                const double d = cfg.limit_distance - state.distance;
+                if (d <= step) {
+                        step = d;
+                        event = EVENT_LIMIT_DISTANCE;
+                }
+        }
+
+        const double sgn = (cfg.direction == MODE_FORWARD) ? 1. : -1.;
+        position[0] += step * sgn * direction[0];
+        position[1] += step * sgn * direction[1];
+        position[2] += step * sgn * direction[2];
+
+        /* Change of medium? */
+        int end_medium = -1;
+        medium_locate(geo, cfg.direction, state, true, &end_medium, false, 0);
+        double end_position[3] = { position[0], position[1], position[2] };
+        if (end_medium != medium) {
+                if (step_max_type == STEP_CHECK) {
+                        const double step_min =
+                            (step < STEP_MIN) ? step : STEP_MIN;
+                        double pi[3] = { position[0], position[1],
+                                position[2] };
+                        double s1 = 0., s2 = -step_min;
+                        position[0] = pi[0] + s2 * sgn * direction[0];
+                        position[1] = pi[1] + s2 * sgn * direction[1];
+                        position[2] = pi[2] + s2 * sgn * direction[2];
+                        int tmp_medium = -1;
+                        medium_locate(geo, cfg.direction, state, true,
+                            &tmp_medium, false, 0);
+                        if (tmp_medium != medium) {
+                                if (tmp_medium != end_medium)
+                                        end_medium = tmp_medium;
+                                s1 = s2;
+                                s2 = -step;
+                                while (fabs(s1 - s2) > STEP_MIN) {
+                                        const double s3 = 0.5 * (s1 + s2);
+                                        position[0] =
+                                            pi[0] + s3 * sgn * direction[0];
+                                        position[1] =
+                                            pi[1] + s3 * sgn * direction[1];
+                                        position[2] =
+                                            pi[2] + s3 * sgn * direction[2];
+                                        tmp_medium = -1;
+                                        medium_locate(geo, cfg.direction, state,
+                                            true, &tmp_medium, false, 0);
+                                        if (tmp_medium == medium) {
+                                                s2 = s3;
+                                        } else {
+                                                s1 = s3;
+                                                if (tmp_medium != end_medium)
+                                                        end_medium = tmp_medium;
+                                        }
+                                }
+                                position[0] = pi[0] + s2 * sgn * direction[0];
+                                position[1] = pi[1] + s2 * sgn * direction[1];
+                                position[2] = pi[2] + s2 * sgn * direction[2];
+                                step += s1;
+                                end_position[0] =
+                                    pi[0] + s1 * sgn * direction[0];
+                                end_position[1] =
+                                    pi[1] + s1 * sgn * direction[1];
+                                end_position[2] =
+                                    pi[2] + s1 * sgn * direction[2];
+                                /* (The reference calls the medium function
+                                 * once more here; it has no side effect.) */
+                        }
+                }
+                event = EVENT_MEDIUM;
+                *out_medium = end_medium;
+        }
+
+        /* End step locals. */
+        double Bi[3] = { 0., 0., 0. };
+        if (locals.magnetized != 0) {
+                Bi[0] = locals.magnet[0];
+                Bi[1] = locals.magnet[1];
+                Bi[2] = locals.magnet[2];
+        }
+        if ((*step_max_locals > 0.) &&
+            ((step_max_type != STEP_RAW) || (event != EVENT_MEDIUM))) {
+                *step_max_locals =
+                    set_locals(p, geo, cfg.accuracy, medium, state, &locals);
+                if (locals.density <= 0.) {
+                        trk.error = RETURN_DENSITY_ERROR;
+                        return false;
+                }
+        }
+
+        if (event & EVENT_MEDIUM) {
+                position[0] = end_position[0];
+                position[1] = end_position[1];
+                position[2] = end_position[2];
+        }
+
+        /* End step kinetic energy. */
+        double k1 = state.energy, dk = 0.;
+        const double dX = 0.5 * step * (density + locals.density);
+        if ((scheme >= MODE_CSDA) && (scheme <= MODE_MIXED)) {
+                const double X = Xtot - sgn * dX;
+                if ((cfg.direction == MODE_FORWARD) && (X <= trk.step_X_limit)) {
+                        k1 = (cfg.event & EVENT_LIMIT_ENERGY) ?
+                            cfg.limit_energy :
+                            0.;
+                        const double grammage =
+                            state.grammage + Xtot - trk.step_X_limit;
+                        if ((grammage_max <= 0.) || (grammage < grammage_max)) {
+                                grammage_max = grammage;
+                                event = EVENT_LIMIT_ENERGY;
+                        }
+                } else if ((cfg.direction == MODE_BACKWARD) &&
+                    (trk.step_X_limit > 0.) && (X > trk.step_X_limit)) {
+                        k1 = (cfg.event & EVENT_LIMIT_ENERGY) ?
+                            cfg.limit_energy :
+                            0.;
+                        const double grammage =
+                            state.grammage + trk.step_X_limit - Xtot;
+                        if ((grammage_max <= 0.) || (grammage < grammage_max)) {
+                                grammage_max = grammage;
+                                event = EVENT_LIMIT_ENERGY;
+                        }
+                } else if (dX < EPSILON_X * Xtot) {
+                        k1 -= sgn * cel_energy_loss(p, scheme, material, k1) *
+                            dX;
+                        if ((cfg.event & EVENT_LIMIT_ENERGY) &&
+                            (cfg.limit_energy > 0.)) {
+                                if (((cfg.direction == MODE_FORWARD) &&
+                                        (k1 < cfg.limit_energy)) ||
+                                    ((cfg.direction == MODE_BACKWARD) &&
+                                        (k1 > cfg.limit_energy))) {
+                                        k1 = cfg.limit_energy;
+                                        event = EVENT_LIMIT_ENERGY;
+                                }
+                        } else if (k1 < 0.) {
+                                k1 = 0.;
+                        }
+                } else {
+                        k1 = cel_kinetic_energy(p, scheme, material, X);
+                }
+        } else if (scheme == MODE_STRAGGLED) {
+                double ratio;
+                step_fluctuate(p, cfg, trk, rng, state, material, Xtot, dX, &k1,
+                    &ratio);
+                dk = fabs(state.energy - k1);
+
+                double kinetic_limit = -1.;
+                if (cfg.direction == MODE_FORWARD) {
+                        const double kinetic_min =
+                            (cfg.event & EVENT_LIMIT_ENERGY) ?
+                            cfg.limit_energy :
+                            0.;
+                        if (k1 <= kinetic_min) kinetic_limit = kinetic_min;
+                } else {
+                        if ((cfg.event & EVENT_LIMIT_ENERGY) &&
+                            (k1 >= cfg.limit_energy))
+                                kinetic_limit = cfg.limit_energy;
+                }
+                if (kinetic_limit >= 0.) {
+                        const double grammage = state.grammage +
+                            fabs(state.energy - kinetic_limit) / dk * dX;
+                        k1 = kinetic_limit;
+                        if ((grammage_max <= 0.) || (grammage < grammage_max)) {
+                                grammage_max = grammage;
+                                event = EVENT_LIMIT_ENERGY;
+                        }
+                }
+
+                /* Discrete events by thinning. */
+                double Xmax = dX;
+                if (grammage_max > 0.) {
+                        const double dX1 = grammage_max - state.grammage;
+                        if (Xmax > dX1) Xmax = dX1;
+                }
+                double k_x = -1.;
+
+                do {
+                        double xs_del =
+                            del_cross_section(p, material, state.energy);
+                        const double tmp_del =
+                            del_cross_section(p, material, k1);
+                        if (tmp_del > xs_del) xs_del = tmp_del;
+                        if (xs_del <= 0.) break;
+                        const double X_del = -log(rng.uniform()) / xs_del;
+                        if (X_del >= Xmax) break;
+                        const double k_h = cel_kinetic_energy(
+                            p, scheme, material, Xtot - sgn * X_del);
+                        const double k_del = state.energy -
+                            sgn * ratio * fabs(state.energy - k_h);
+                        if (k_del <= 0.) break;
+                        const double r =
+                            del_cross_section(p, material, k_del) / xs_del;
+                        if (rng.uniform() > r) break;
+                        k_x = k_del;
+                        Xmax = X_del;
+                        event = EVENT_VERTEX_DEL;
+                } while (0);
+
+                if (cfg.scattering == MODE_MIXED) {
+                        do {
+                                double kmin, kmax;
+                                if (k1 <= state.energy)
+                                        kmin = k1, kmax = state.energy;
+                                else
+                                        kmax = k1, kmin = state.energy;
+                                if (kmin < p.K[1]) {
+                                        const double tmp = kmin;
+                                        kmin = kmax, kmax = tmp;
+                                }
+                                (void)kmax;
+                                const double lb_ehs =
+                                    coulomb_ehs_length(p, material, kmin);
+                                if (lb_ehs <= 0.) break;
+                                const double X_ehs =
+                                    -log(rng.uniform()) * lb_ehs;
+                                if (X_ehs >= Xmax) break;
+                                const double k_h = cel_kinetic_energy(
+                                    p, scheme, material, Xtot - sgn * X_ehs);
+                                const double k_ehs = state.energy -
+                                    sgn * ratio * fabs(state.energy - k_h);
+                                if (k_ehs <= 0.) break;
+                                const double r =
+                                    coulomb_ehs_length(p, material, k_ehs) /
+                                    lb_ehs;
+                                if ((r <= 0.) || (rng.uniform() > 1. / r))
+                                        break;
+                                k_x = k_ehs;
+                                Xmax = X_ehs;
+                                event = EVENT_VERTEX_COULOMB;
+                        } while (0);
+                }
+
+                if (k_x >= 0.) {
+                        k1 = k_x;
+                        grammage_max = state.grammage + Xmax;
+                }
+        }
+
+        /* Grammage. */
+        const double Xi = state.grammage;
+        state.grammage += dX;
+        const double sf0 = step;
+        double h_int = 0.;
+        if ((grammage_max > 0.) && (state.grammage >= grammage_max)) {
+                const double dX_ = grammage_max - Xi;
+                if ((fabs(density - locals.density) <= (double)FLT_EPSILON) ||
+                    (sf0 <= (double)FLT_EPSILON)) {
+                        step = dX_ * density_i;
+                        h_int = dX_ / (state.grammage - Xi);
+                } else {
+                        const double drho = locals.density - density;
+                        double tmp = density * density + 2. * dX_ * drho / sf0;
+                        tmp = (tmp > (double)FLT_EPSILON) ? sqrt(tmp) : 0;
+                        h_int = (tmp - density) / drho;
+                        step *= h_int;
+                }
+                state.grammage = grammage_max;
+                if (!(event & EVENT_LIMIT_ENERGY)) {
+                        if (scheme <= MODE_MIXED) {
+                                if (scheme != MODE_DISABLED)
+                                        k1 = cel_kinetic_energy(p, scheme,
+                                            material,
+                                            Xtot - sgn * (state.grammage - Xi));
+                                event = trk.step_foreseen;
+                        } else if (!(event &
+                                       (EVENT_VERTEX_COULOMB |
+                                           EVENT_VERTEX_DEL))) {
+                                k1 = state.energy -
+                                    sgn * (state.grammage - Xi) * dk / dX;
+                                if (k1 < 0.) k1 = 0.;
+                                event = EVENT_LIMIT_GRAMMAGE;
+                        }
+                }
+
+                const double ds_ = step - sf0;
+                position[0] += ds_ * sgn * direction[0];
+                position[1] += ds_ * sgn * direction[1];
+                position[2] += ds_ * sgn * direction[2];
+        }
+
+        /* Proper time. */
+        int decayed = 0;
+        double time_max = (cfg.event & EVENT_LIMIT_TIME) ? cfg.limit_time : 0.;
+        if (cfg.decay == MODE_RANDOMISED) {
+                if ((time_max <= 0.) || (trk.lifetime < time_max)) {
+                        time_max = trk.lifetime;
+                        decayed = 1;
+                }
+        }
+
+        const double sf1 = step;
+        if (straight && (scheme != MODE_DISABLED)) {
+                const double Ti =
+                    cel_proper_time(p, scheme, material, state.energy);
+                if (time_max > 0.) {
+                        const double Tf =
+                            Ti - sgn * (time_max - state.time) * density;
+                        if (Tf > 0.) {
+                                const double dxT = fabs(Xtot -
+                                    cel_grammage_as_time(
+                                        p, scheme, material, Tf));
+                                if (Xi + dxT < state.grammage) {
+                                        event = EVENT_LIMIT_TIME;
+                                        state.time = time_max;
+                                        state.decayed = decayed;
+                                        step = dxT * density_i;
+                                        if (step > sf1) step = sf1;
+                                        state.grammage = Xi + dxT;
+                                        const double xf = Xtot - sgn * dxT;
+                                        k1 = cel_kinetic_energy(
+                                            p, scheme, material, xf);
+                                }
+                        }
+                }
+
+                if (event != EVENT_LIMIT_TIME) {
+                        const double Tf =
+                            cel_proper_time(p, scheme, material, k1);
+                        state.time += fabs(Tf - Ti) * density_i;
+                }
+        } else {
+                const double p_f =
+                    (k1 <= 0) ? momentum : sqrt(k1 * (k1 + 2. * p.mass));
+                const double ti = state.time;
+                state.time += 0.5 * step * p.mass * (1. / momentum + 1. / p_f);
+                if ((time_max > 0.) && (state.time >= time_max)) {
+                        event = EVENT_LIMIT_TIME;
+                        state.time = time_max;
+                        state.decayed = decayed;
+
+                        const double a = (momentum / p_f - 1.) / sf1;
+                        const double c =
+                            -2. * (time_max - ti) * momentum / p.mass;
+                        if (a != 0.) {
+                                double delta = 1. - a * c;
+                                if (delta < 0.) delta = 0.;
+                                step = 1. / a * (sqrt(delta) - 1.);
+                        } else {
+                                step = -0.5 * c;
+                        }
+                        if (step < 0.) step = 0.;
+
+                        if (scheme != MODE_DISABLED) {
+                                const double p1 = momentum / (1 + a * step);
+                                k1 = sqrt(p1 * p1 - p.mass * p.mass) - p.mass;
+                                if (k1 < 0.) k1 = 0.;
+                        }
+
+                        const double Xf = Xi + dX;
+                        if (density == locals.density)
+                                state.grammage = Xi + step * density;
+                        else
+                                state.grammage = Xi +
+                                    step *
+                                        (density +
+                                            0.5 * step / sf0 *
+                                                (locals.density - density));
+                        if (state.grammage > Xf) state.grammage = Xf;
+                }
+        }
+
+        if (event == EVENT_LIMIT_TIME) {
+                const double ds_ = step - sf1;
+                position[0] += ds_ * sgn * direction[0];
+                position[1] += ds_ * sgn * direction[1];
+                position[2] += ds_ * sgn * direction[2];
+        }
+
+        trk.step_event = event;
+        state.energy = k1;
+        state.distance += step;
+
+        /* End of step multiple scattering path length. */
+        if (cfg.scattering == MODE_MIXED) {
+                double mu0, invlb1_;
+                if (state.energy <= 0.) {
+                        trk.step_invlb1 = invlb1;
+                } else {
+                        table_get_msc(p, cfg.energy_loss, material,
+                            state.energy, &mu0, &invlb1_);
+                        trk.step_invlb1 = locals.density * invlb1_;
+                }
+        }
+
+        /* End of step magnetic field. */
+        double rLarmor1 = 0., uT1[3] = { 0., 0., 0. };
+        if (locals.magnetized) {
+                double B[3] = { locals.magnet[0], locals.magnet[1],
+                        locals.magnet[2] };
+                int magnetized = locals.magnetized;
+                if (h_int > 0.) {
+                        B[0] = Bi[0] + h_int * (B[0] - Bi[0]);
+                        B[1] = Bi[1] + h_int * (B[1] - Bi[1]);
+                        B[2] = Bi[2] + h_int * (B[2] - Bi[2]);
+                        /* Sic: the reference inverts the flag here
+                         * (pumas.c:6843-6844); kept for parity. */
+                        magnetized =
+                            (B[0] * B[0] + B[1] * B[1] + B[2] * B[2] == 0.);
+                }
+
+                if (magnetized == 0) {
+                        rLarmor1 = 0.;
+                        uT1[0] = uT1[1] = uT1[2] = 0.;
+                } else {
+                        uT1[0] = direction[1] * B[2] - direction[2] * B[1];
+                        uT1[1] = direction[2] * B[0] - direction[0] * B[2];
+                        uT1[2] = direction[0] * B[1] - direction[1] * B[0];
+                        const double BT = sqrt(
+                            uT1[0] * uT1[0] + uT1[1] * uT1[1] + uT1[2] * uT1[2]);
+                        if (BT == 0.) {
+                                rLarmor1 = 0.;
+                        } else {
+                                const double pp = (state.energy <= 0) ?
+                                    momentum :
+                                    sqrt(state.energy *
+                                        (state.energy + 2. * p.mass));
+                                rLarmor1 = pp / (BT * LARMOR_FACTOR);
+                                const double pinv = 1. / pp;
+                                uT1[0] *= pinv;
+                                uT1[1] *= pinv;
+                                uT1[2] *= pinv;
+                        }
+                }
+        }
+
+        /* Magnetic deflection. */
+        if ((rLarmor0 > 0.) || (rLarmor1 > 0.)) {
+                const double u[3] = { direction[0], direction[1],
+                        direction[2] };
+                const double theta0 =
+                    (rLarmor0 > 0.) ? state.charge * step / rLarmor0 : 0.;
+                const double theta1 =
+                    (rLarmor1 > 0.) ? state.charge * step / rLarmor1 : 0.;
+                double theta = 0.5 * (theta0 + theta1);
+                if (cfg.direction == MODE_BACKWARD) theta = -theta;
+                double c = cos(theta);
+                double s = sin(theta);
+                double v[3];
+                int i;
+                for (i = 0; i < 3; i++) v[i] = 0.5 * (uT0[i] + uT1[i]);
+                double nrmv = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+                if (nrmv > 0.) {
+                        nrmv = 1. / sqrt(nrmv);
+                        for (i = 0; i < 3; i++) v[i] *= nrmv;
+                } else {
+                        c = 1.;
+                        s = 0.;
+                }
+                for (i = 0; i < 3; i++) direction[i] = c * u[i] + s * v[i];
+
+                const double norm = 1. /
+                    sqrt(direction[0] * direction[0] +
+                        direction[1] * direction[1] +
+                        direction[2] * direction[2]);
+                for (i = 0; i < 3; i++) direction[i] *= norm;
+        }
+
+        /* Soft multiple scattering. */
+        if ((invlb1 > 0.) || (trk.step_invlb1 > 0.)) {
+                double ilb1 = 0.25 * step * (invlb1 + trk.step_invlb1);
+                if (ilb1 > 1.) ilb1 = 1.;
+                double mu;
+                do {
+                        mu = -ilb1 * log(rng.uniform());
+                } while (mu > 1.);
+                step_rotate_direction(rng, state, mu);
+        }
+
+        return true;
+}
+
+PB_FN int straight_flag(
+    const Settings & cfg, double step_max_locals, const Locals & locals)
+{
+        return ((cfg.scattering == MODE_DISABLED) &&
+                   (cfg.energy_loss <= MODE_MIXED) && (step_max_locals <= 0.) &&
+                   !locals.magnetized) ?
+            1 :
+            0;
+}
+
+/* pumas.c:5194-5514 */
+template <class Rng>
+PB_FN int transport_with_stepping(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Track & trk, Rng & rng, State & state,
+    int * medium_ptr, Locals & locals, double step_max_medium,
+    int step_max_type, double step_max_locals)
+{
+        int medium = *medium_ptr;
+        int material = geo.layer[medium].material;
+
+        const int scheme = cfg.energy_loss;
+        int straight = straight_flag(cfg, step_max_locals, locals);
+
+        trk.step_event = EVENT_NONE;
+
+        double ti = state.time;
+        double wi = state.weight;
+        double Xi = state.grammage;
+        double dei, Xf;
+        if (scheme > MODE_DISABLED) {
+                const double ki = state.energy;
+                Xf = cel_grammage(p, scheme, material, ki);
+                dei = 1. / cel_energy_loss(p, scheme, material, ki);
+        } else {
+                Xf = dei = 0.;
+        }
+
+        if ((cfg.event & EVENT_LIMIT_DISTANCE) &&
+            (state.distance >= cfg.limit_distance))
+                return EVENT_LIMIT_DISTANCE;
+        if ((cfg.event & EVENT_LIMIT_GRAMMAGE) &&
+            (state.grammage >= cfg.limit_grammage))
+                return EVENT_LIMIT_GRAMMAGE;
+        if ((cfg.event & EVENT_LIMIT_TIME) && (state.time >= cfg.limit_time))
+                return EVENT_LIMIT_TIME;
+        if (state.weight <= 0.) return EVENT_WEIGHT;
+
+        double grammage_max;
+        trk.step_event = EVENT_NONE;
+        trk.step_first = 1;
+        trk.step_X_limit = (cfg.event & EVENT_LIMIT_ENERGY) ?
+            cel_grammage(p, (scheme > MODE_DISABLED) ? scheme : MODE_CSDA,
+                material, cfg.limit_energy) :
+            0.;
+        trk.step_invlb1 = 0;
+        transport_limit(p, cfg, trk, rng, state, material, Xi, Xf, &grammage_max);
+        if (trk.step_event) return trk.step_event;
+
+        int step_index = 1;
+        for (;;) {
+                if (step_index > 1) {
+                        step_max_type = medium_locate(geo, cfg.direction, state,
+                            false, 0, true, &step_max_medium);
+                        if ((step_max_medium > 0.) &&
+                            (step_max_type == STEP_CHECK))
+                                step_max_medium += 0.5 * STEP_MIN;
+                }
+
+                int new_medium = -1;
+                if (!step_transport(p, cfg, geo, trk, rng, state, straight,
+                        medium, locals, grammage_max, step_max_medium,
+                        step_max_type, &step_max_locals, &new_medium))
+                        return trk.step_event;
+                step_index++;
+
+                if (!trk.step_event) continue;
+
+                /* Weight update at a boundary or hard loss. */
+                if ((cfg.direction == MODE_BACKWARD) &&
+                    (cfg.energy_loss >= MODE_CSDA)) {
+                        const double wt = (cfg.decay == MODE_WEIGHTED) ?
+                            exp(-fabs(state.time - ti) / p.ctau) :
+                            1.;
+                        state.weight = wi * wt * dei *
+                            cel_energy_loss(p, scheme, material, state.energy);
+                } else if (cfg.decay == MODE_WEIGHTED) {
+                        state.weight =
+                            wi * exp(-fabs(state.time - ti) / p.ctau);
+                }
+
+                if (trk.step_event &
+                    (EVENT_LIMIT | EVENT_WEIGHT | EVENT_VERTEX_DECAY)) {
+                        break;
+                } else if (trk.step_event &
+                    (EVENT_VERTEX_DEL | EVENT_VERTEX_COULOMB)) {
+                        if (trk.step_event & EVENT_VERTEX_DEL) {
+                                transport_do_del(
+                                    p, cfg, trk, rng, state, material);
+                                if ((cfg.event & trk.step_event) ||
+                                    trk.step_event == EVENT_WEIGHT)
+                                        break;
+                                trk.step_first = 1;
+                                trk.step_invlb1 = 0;
+                        } else {
+                                transport_do_ehs(p, cfg, rng, state, material);
+                                if (cfg.event & trk.step_event) break;
+                        }
+
+                        if (step_max_locals > 0.) {
+                                step_max_locals = set_locals(p, geo,
+                                    cfg.accuracy, medium, state, &locals);
+                                if (locals.density <= 0.) {
+                                        trk.error = RETURN_DENSITY_ERROR;
+                                        return trk.step_event;
+                                }
+                        }
+                } else if (trk.step_event & EVENT_MEDIUM) {
+                        medium = new_medium;
+                        if ((medium < 0) || (cfg.event & EVENT_MEDIUM)) break;
+                        material = geo.layer[medium].material;
+                        locals.density = 0.;
+                        locals.magnet[0] = locals.magnet[1] =
+                            locals.magnet[2] = 0.;
+                        locals.magnetized = 0;
+                        step_max_locals = set_locals(
+                            p, geo, cfg.accuracy, medium, state, &locals);
+                        if (locals.density <= 0.) {
+                                trk.error = RETURN_DENSITY_ERROR;
+                                return trk.step_event;
+                        }
+                        straight = straight_flag(cfg, step_max_locals, locals);
+
+                        const int tmp_scheme =
+                            scheme > MODE_DISABLED ? scheme : MODE_CSDA;
+                        trk.step_X_limit = (cfg.event & EVENT_LIMIT_ENERGY) ?
+                            cel_grammage(
+                                p, tmp_scheme, material, cfg.limit_energy) :
+                            0.;
+                        trk.step_first = 1;
+                        trk.step_invlb1 = 0;
+                }
+
+                ti = state.time;
+                wi = state.weight;
+                Xi = state.grammage;
+                if (cfg.energy_loss >= MODE_CSDA) {
+                        const double ki = state.energy;
+                        Xf = cel_grammage(p, scheme, material, ki);
+                        dei = 1. / cel_energy_loss(p, scheme, material, ki);
+                }
+                transport_limit(
+                    p, cfg, trk, rng, state, material, Xi, Xf, &grammage_max);
+                if (trk.step_event) break;
+        }
+
+        /* Protect the final kinetic energy against rounding errors. */
+        if (cfg.direction == MODE_FORWARD) {
+                const double kinetic_min =
+                    (cfg.event & EVENT_LIMIT_ENERGY) ? cfg.limit_energy : 0.;
+                if (fabs(state.energy - kinetic_min) < (double)FLT_EPSILON)
+                        state.energy = kinetic_min;
+        } else {
+                if ((cfg.event & EVENT_LIMIT_ENERGY) &&
+                    (fabs(state.energy - cfg.limit_energy) <
+                        (double)FLT_EPSILON))
+                        state.energy = cfg.limit_energy;
+        }
+
+        *medium_ptr = medium;
+        return trk.step_event;
+}
+
+/* Closed form CSDA in a uniform, field free medium. pumas.c:4777-4949. */
+PB_FN int transport_with_csda(const Physics & p, const Settings & cfg,
+    const Geometry & geo, const Track & trk, State & state, int medium,
+    const Locals & locals)
+{
+        const int material = geo.layer[medium].material;
+        const double density = locals.density;
+        const double ki = state.energy;
+        const double di = state.distance;
+        const double ti = state.time;
+        const double xi = cel_grammage(p, MODE_CSDA, material, ki);
+        const double Ti = cel_proper_time(p, MODE_CSDA, material, ki);
+
+        int event = EVENT_NONE;
+        double xB;
+        if (cfg.event & EVENT_LIMIT_GRAMMAGE) {
+                xB = cfg.limit_grammage - state.grammage;
+                event = EVENT_LIMIT_GRAMMAGE;
+        } else
+                xB = DBL_MAX;
+        if (cfg.event & EVENT_LIMIT_DISTANCE) {
+                const double xD = density * (cfg.limit_distance - di);
+                if (xD < xB) {
+                        xB = xD;
+                        event = EVENT_LIMIT_DISTANCE;
+                }
+        }
+        int decayed = 0;
+        double time_max = (cfg.event & EVENT_LIMIT_TIME) ? cfg.limit_time : 0.;
+        if (cfg.decay == MODE_RANDOMISED) {
+                if ((time_max <= 0.) || (trk.lifetime < time_max)) {
+                        time_max = trk.lifetime;
+                        decayed = 1;
+                }
+        }
+        if (time_max > 0.) {
+                const double dt = time_max - ti;
+                if (dt <= 0.) {
+                        xB = 0.;
+                        event = EVENT_LIMIT_TIME;
+                } else {
+                        const double sgn =
+                            (cfg.direction == MODE_FORWARD) ? 1. : -1.;
+                        const double Tf = Ti - sgn * dt * density;
+                        if (Tf > 0.) {
+                                const double xT = fabs(xi -
+                                    cel_grammage_as_time(
+                                        p, MODE_CSDA, material, Tf));
+                                if (xT < xB) {
+                                        xB = xT;
+                                        event = EVENT_LIMIT_TIME;
+                                }
+                        }
+                }
+        }
+        if (xB <= 0.) return event;
+
+        double xf, kf;
+        if (cfg.direction == MODE_FORWARD) {
+                if (xi > xB) {
+                        xf = xi - xB;
+                        if (xB < EPSILON_X * xi) {
+                                kf = ki -
+                                    cel_energy_loss(p, MODE_CSDA, material, ki) *
+                                        xB;
+                                if (kf < 0.) kf = 0.;
+                        } else {
+                                kf = cel_kinetic_energy(
+                                    p, MODE_CSDA, material, xf);
+                        }
+                } else {
+                        xf = kf = 0.;
+                        event = EVENT_LIMIT_ENERGY;
+                }
+
+                if (cfg.event & EVENT_LIMIT_ENERGY) {
+                        if (ki <= cfg.limit_energy) return EVENT_LIMIT_ENERGY;
+                        if (kf < cfg.limit_energy) {
+                                kf = cfg.limit_energy;
+                                xf = cel_grammage(p, MODE_CSDA, material, kf);
+                                event = EVENT_LIMIT_ENERGY;
+                        }
+                }
+        } else {
+                if (xB == DBL_MAX) {
+                        xf = xB;
+                        kf = DBL_MAX;
+                } else {
+                        xf = xB + xi;
+                        if (xB < EPSILON_X * xi) {
+                                kf = ki +
+                                    cel_energy_loss(p, MODE_CSDA, material, ki) *
+                                        xB;
+                        } else {
+                                kf = cel_kinetic_energy(
+                                    p, MODE_CSDA, material, xf);
+                        }
+                }
+                if (cfg.event & EVENT_LIMIT_ENERGY) {
+                        if (ki >= cfg.limit_energy) return EVENT_LIMIT_ENERGY;
+                        if (kf > cfg.limit_energy) {
+                                kf = cfg.limit_energy;
+                                xf = cel_grammage(p, MODE_CSDA, material, kf);
+                                event = EVENT_LIMIT_ENERGY;
+                        }
+                }
+        }
+
+        const double distance = fabs(xf - xi) / density;
+        state.energy = kf;
+        if (event == EVENT_LIMIT_DISTANCE)
+                state.distance = cfg.limit_distance;
+        else
+                state.distance += distance;
+        if (event == EVENT_LIMIT_GRAMMAGE)
+                state.grammage = cfg.limit_grammage;
+        else
+                state.grammage += distance * density;
+        if (event == EVENT_LIMIT_TIME) {
+                state.time = time_max;
+                state.decayed = decayed;
+                if (decayed) event = EVENT_VERTEX_DECAY;
+        } else
+                state.time +=
+                    fabs(Ti - cel_proper_time(p, MODE_CSDA, material, kf)) /
+                    density;
+        if (cfg.direction == MODE_BACKWARD)
+                state.weight *= cel_energy_loss(p, MODE_CSDA, material, kf) /
+                    cel_energy_loss(p, MODE_CSDA, material, ki);
+        if (cfg.decay == MODE_WEIGHTED)
+                state.weight *= exp(-fabs(ti - state.time) / p.ctau);
+
+        double path;
+        if (cfg.direction == MODE_FORWARD)
+                path = distance;
+        else
+                path = -distance;
+        state.position[0] += path * state.direction[0];
+        state.position[1] += path * state.direction[1];
+        state.position[2] += path * state.direction[2];
+
+        return event;
+}
+
+/* Result of one track: the reference's return code, event and media[2]. */
+struct Outcome {
+        int rc;
+        int event;
+        int medium[2];
+};
+
+/* Batch level validation, pumas.c:3152-3177 (done once on the host). */
+PB_FN int settings_check(const Physics & p, const Settings & cfg)
+{
+        if ((p.particle == 1) && (cfg.direction == MODE_FORWARD) &&
+            (cfg.decay == MODE_WEIGHTED))
+                return 3; /* PUMAS_RETURN_DECAY_ERROR */
+        if ((cfg.accuracy <= 0) || (cfg.accuracy > 1))
+                return 1; /* PUMAS_RETURN_ACCURACY_ERROR */
+        if ((cfg.direction == MODE_BACKWARD) &&
+            (cfg.energy_loss > MODE_CSDA) && (p.cutoff < 1E-02))
+                return 1;
+        return 0;
+}
+
+/* pumas_context_transport for one track, pumas.c:3114-3251. */
+template <class Rng>
+PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Rng & rng, State & state, unsigned int * n_steps)
+{
+        Outcome out;
+        out.rc = RETURN_SUCCESS;
+        out.event = EVENT_NONE;
+        out.medium[0] = out.medium[1] = -1;
+        if (n_steps) *n_steps = 0;
+
+        if (state.decayed) {
+                out.event = EVENT_VERTEX_DECAY;
+                return out;
+        }
+
+        {
+                const double * const u = state.direction;
+                const double norm2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+                if (fabs(norm2 - 1) > (double)FLT_EPSILON) {
+                        out.rc = 5; /* PUMAS_RETURN_DIRECTION_ERROR */
+                        return out;
+                }
+        }
+
+        Track trk;
+        trk.lifetime = 0.;
+        trk.step_first = 1;
+        trk.step_event = EVENT_NONE;
+        trk.step_foreseen = EVENT_NONE;
+        trk.step_X_limit = 0.;
+        trk.step_invlb1 = 0.;
+        trk.randn_done = 0;
+        trk.randn_next = 0.;
+        trk.error = RETURN_SUCCESS;
+        trk.n_steps = 0;
+
+        int medium = -1;
+        double step_max_medium = 0.;
+        const int step_max_type = medium_locate(
+            geo, cfg.direction, state, true, &medium, true, &step_max_medium);
+        out.medium[0] = medium;
+        out.medium[1] = -1;
+        if (medium < 0) {
+                out.event = EVENT_MEDIUM;
+                return out;
+        } else if ((step_max_medium > 0.) && (step_max_type == STEP_CHECK))
+                step_max_medium += 0.5 * STEP_MIN;
+        Locals locals;
+        locals.density = 0.;
+        locals.magnet[0] = locals.magnet[1] = locals.magnet[2] = 0.;
+        locals.magnetized = 0;
+        const double step_max_locals =
+            set_locals(p, geo, cfg.accuracy, medium, state, &locals);
+        if ((step_max_locals > 0.) && (step_max_locals < step_max_medium))
+                step_max_medium = step_max_locals;
+        if (locals.density <= 0.) {
+                out.rc = RETURN_DENSITY_ERROR;
+                return out;
+        }
+
+        if (cfg.decay == MODE_RANDOMISED) {
+                const double u = rng.uniform();
+                trk.lifetime = state.time - p.ctau * log(u);
+        }
+
+        int do_stepping = 1;
+        if ((step_max_medium <= 0.) && (step_max_locals <= 0.) &&
+            (cfg.energy_loss <= MODE_CSDA)) {
+                if ((cfg.energy_loss == MODE_DISABLED) &&
+                    ((cfg.event & EVENT_LIMIT) == 0)) {
+                        out.rc = 15; /* PUMAS_RETURN_MISSING_LIMIT */
+                        return out;
+                } else if ((cfg.scattering == MODE_DISABLED) &&
+                    (cfg.energy_loss == MODE_CSDA) && !locals.magnetized) {
+                        /* (magnetised closed form: stepping instead, see the
+                         * header comment) */
+                        do_stepping = 0;
+                }
+        }
+
+        int e;
+        if (do_stepping) {
+                e = transport_with_stepping(p, cfg, geo, trk, rng, state,
+                    &medium, locals, step_max_medium, step_max_type,
+                    step_max_locals);
+        } else {
+                e = transport_with_csda(p, cfg, geo, trk, state, medium, locals);
+        }
+        out.event = e;
+        out.medium[1] = medium;
+        out.rc = trk.error;
+        if (n_steps) *n_steps = trk.n_steps;
+        return out;
+}
+
+} /* namespace pb */
+
+#endif
