@@ -1,0 +1,1207 @@
+/*
+ * cabi.cu -- the C ABI of libpumas_b200.so (include/pumas_b200.h).
+ *
+ * Host side of the drop-in boundary: physics load / dump, contexts, property
+ * getters, the error machinery of the reference (src/pumas.c:203-270,
+ * 2299-2327, 7814-7859) and the transport entry points, which stage the
+ * states through HBM and launch the kernels of kernels.cu. There is no CPU
+ * transport path in this library: without a usable CUDA device the transport
+ * entry points fail with PUMAS_RETURN_INTERNAL_ERROR.
+ */
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+#include "pb_dump.hpp"
+#include "pb_tables.h"
+#include "pumas_b200.h"
+
+/* ---- opaque objects ------------------------------------------------------ */
+struct pumas_physics {
+        pb::HostPhysics host;
+        /* Device copy of host.image, created on first use. */
+        std::mutex mutex;
+        int device;
+        void * d_image;
+        pb::Physics d_view;
+};
+
+namespace {
+
+/* struct simulation_context (pumas.c:426-477): the public struct comes first
+ * so that `struct pumas_context *` is a pointer to this object. */
+struct ContextImpl {
+        struct pumas_context api;
+        const pumas_physics * physics;
+        unsigned long seed;
+        int seed_set;
+        unsigned long long track_offset;
+        int has_geometry;
+        struct pumas_b200_geometry geometry;
+        cudaStream_t stream;
+        /* device staging buffers (grown on demand) */
+        long capacity;
+        pb::State * d_states;
+        int * d_events;
+        int * d_media;
+        unsigned int * d_random;
+        unsigned int * d_steps;
+        int * d_status;
+        long last_n;
+        double last_ms;
+        int last_launches;
+        cudaEvent_t ev0, ev1;
+        int events_ready;
+        int extra_memory;
+        /* user memory follows */
+        double data[1];
+};
+
+/* ---- error machinery, pumas.c:203-270, 2299-2327, 7814-7859 --------------- */
+void default_handler(
+    enum pumas_return rc, pumas_function_t * caller, const char * message)
+{
+        (void)rc;
+        (void)caller;
+        fputs("pumas: library error. See details below\n", stderr);
+        fprintf(stderr, "error: %s\n", message);
+        exit(EXIT_FAILURE);
+}
+
+struct {
+        pumas_handler_cb * handler = &default_handler;
+        int catch_ = 0;
+        int caught_code = PUMAS_RETURN_SUCCESS;
+        pumas_function_t * caught_function = nullptr;
+        char caught_message[1024];
+} g_error;
+
+#define FN(f) ((pumas_function_t *)(f))
+
+enum pumas_return raise(pumas_function_t * caller, enum pumas_return rc,
+    const char * file, int line, const char * fmt, ...)
+{
+        if (rc == PUMAS_RETURN_SUCCESS) return rc;
+        char text[768];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(text, sizeof text, fmt, ap);
+        va_end(ap);
+        char message[1024];
+        const char * name = pumas_error_function(caller);
+        snprintf(message, sizeof message, "{ %s [#%d], %s:%d } %s",
+            (name != nullptr) ? name : "?", (int)rc, file, line, text);
+
+        if (g_error.catch_) {
+                if (g_error.caught_code == PUMAS_RETURN_SUCCESS) {
+                        g_error.caught_code = rc;
+                        g_error.caught_function = caller;
+                        snprintf(g_error.caught_message,
+                            sizeof g_error.caught_message, "%s", message);
+                }
+                return rc;
+        }
+        if (g_error.handler != nullptr) g_error.handler(rc, caller, message);
+        return rc;
+}
+
+#define RAISE(f, rc, ...) raise(FN(f), rc, __FILE__, __LINE__, __VA_ARGS__)
+
+/* ---- device helpers -------------------------------------------------------- */
+int device_usable(std::string * why)
+{
+        int count = 0;
+        const cudaError_t e = cudaGetDeviceCount(&count);
+        if ((e != cudaSuccess) || (count <= 0)) {
+                cudaGetLastError();
+                if (why)
+                        *why = std::string("no CUDA device (") +
+                            cudaGetErrorString(e) + ")";
+                return 0;
+        }
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) {
+                cudaGetLastError();
+                if (why) *why = "cannot query the CUDA device";
+                return 0;
+        }
+        if (prop.major != 10) {
+                if (why)
+                        *why = std::string("device `") + prop.name +
+                            "' is not an sm_100 (B200) part; this library "
+                            "carries sm_100a code only";
+                return 0;
+        }
+        return 1;
+}
+
+enum pumas_return physics_upload(
+    pumas_function_t * caller, pumas_physics * physics)
+{
+        std::lock_guard<std::mutex> lock(physics->mutex);
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if ((physics->d_image != nullptr) && (physics->device == dev))
+                return PUMAS_RETURN_SUCCESS;
+        if (physics->d_image != nullptr) {
+                /* A physics object serves one device per process (one process
+                 * per GPU); re-home it if the device changed. */
+                cudaFree(physics->d_image);
+                physics->d_image = nullptr;
+        }
+        const size_t size = physics->host.image.size();
+        cudaError_t e = cudaMalloc(&physics->d_image, size);
+        if (e == cudaSuccess)
+                e = cudaMemcpy(physics->d_image, physics->host.image.data(),
+                    size, cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+                physics->d_image = nullptr;
+                return raise(caller, PUMAS_RETURN_MEMORY_ERROR, __FILE__,
+                    __LINE__, "could not upload the physics tables (%s)",
+                    cudaGetErrorString(e));
+        }
+        physics->device = dev;
+        physics->d_view = physics->host.view_at(physics->d_image);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+void context_free_buffers(ContextImpl * c)
+{
+        if (c->d_states) cudaFree(c->d_states);
+        if (c->d_events) cudaFree(c->d_events);
+        if (c->d_media) cudaFree(c->d_media);
+        if (c->d_random) cudaFree(c->d_random);
+        if (c->d_steps) cudaFree(c->d_steps);
+        c->d_states = nullptr;
+        c->d_events = nullptr;
+        c->d_media = nullptr;
+        c->d_random = nullptr;
+        c->d_steps = nullptr;
+        c->capacity = 0;
+}
+
+cudaError_t context_reserve(ContextImpl * c, long n)
+{
+        cudaError_t e = cudaSuccess;
+        if (c->d_status == nullptr) {
+                e = cudaMalloc(&c->d_status, sizeof(int));
+                if (e != cudaSuccess) return e;
+        }
+        if (!c->events_ready) {
+                e = cudaEventCreate(&c->ev0);
+                if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
+                if (e != cudaSuccess) return e;
+                c->events_ready = 1;
+        }
+        if (n <= c->capacity) return cudaSuccess;
+        context_free_buffers(c);
+        e = cudaMalloc(&c->d_states, n * sizeof(pb::State));
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_events, n * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_media, 2 * n * sizeof(int));
+        if (e == cudaSuccess)
+                e = cudaMalloc(&c->d_random, n * sizeof(unsigned int));
+        if (e == cudaSuccess)
+                e = cudaMalloc(&c->d_steps, n * sizeof(unsigned int));
+        if (e != cudaSuccess) {
+                context_free_buffers(c);
+                return e;
+        }
+        c->capacity = n;
+        return cudaSuccess;
+}
+
+bool is_device_pointer(const void * ptr)
+{
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, ptr) != cudaSuccess) {
+                cudaGetLastError();
+                return false;
+        }
+        return (attr.type == cudaMemoryTypeDevice) ||
+            (attr.type == cudaMemoryTypeManaged);
+}
+
+pb::Settings settings_from(const struct pumas_context * c)
+{
+        pb::Settings s;
+        s.energy_loss = (int)c->mode.energy_loss;
+        s.decay = (int)c->mode.decay;
+        s.direction = (int)c->mode.direction;
+        s.scattering = (int)c->mode.scattering;
+        s.event = (int)c->event;
+        s.limit_energy = c->limit.energy;
+        s.limit_distance = c->limit.distance;
+        s.limit_grammage = c->limit.grammage;
+        s.limit_time = c->limit.time;
+        s.accuracy = c->accuracy;
+        return s;
+}
+
+const char * return_text(int rc)
+{
+        switch (rc) {
+        case PUMAS_RETURN_DENSITY_ERROR:
+                return "negative density";
+        case PUMAS_RETURN_DIRECTION_ERROR:
+                return "bad norm for state direction";
+        case PUMAS_RETURN_MISSING_LIMIT:
+                return "infinite medium without external limit(s)";
+        default:
+                return "transport error";
+        }
+}
+
+} /* namespace */
+
+extern "C" {
+
+/* ---- errors ---------------------------------------------------------------- */
+void pumas_error_handler_set(pumas_handler_cb * handler)
+{
+        g_error.handler = handler;
+}
+
+pumas_handler_cb * pumas_error_handler_get(void) { return g_error.handler; }
+
+void pumas_error_catch(int enable)
+{
+        if (enable) {
+                g_error.catch_ = 1;
+                g_error.caught_code = PUMAS_RETURN_SUCCESS;
+                g_error.caught_function = nullptr;
+        } else {
+                g_error.catch_ = 0;
+        }
+}
+
+enum pumas_return pumas_error_raise(void)
+{
+        if (g_error.catch_ == 0) {
+                return RAISE(pumas_error_raise, PUMAS_RETURN_RAISE_ERROR,
+                    "`pumas_error_raise' called with no catch");
+        }
+        g_error.catch_ = 0;
+        const enum pumas_return rc = (enum pumas_return)g_error.caught_code;
+        if ((rc != PUMAS_RETURN_SUCCESS) && (g_error.handler != nullptr))
+                g_error.handler(
+                    rc, g_error.caught_function, g_error.caught_message);
+        g_error.caught_code = PUMAS_RETURN_SUCCESS;
+        return rc;
+}
+
+const char * pumas_error_function(pumas_function_t * caller)
+{
+#define NAME(f)                                                                \
+        if (caller == FN(f)) return #f;
+        NAME(pumas_physics_load)
+        NAME(pumas_physics_dump)
+        NAME(pumas_physics_create)
+        NAME(pumas_physics_particle)
+        NAME(pumas_physics_property_range)
+        NAME(pumas_physics_property_proper_time)
+        NAME(pumas_physics_property_magnetic_rotation)
+        NAME(pumas_physics_property_kinetic_energy)
+        NAME(pumas_physics_property_stopping_power)
+        NAME(pumas_physics_property_energy_straggling)
+        NAME(pumas_physics_property_elastic_cutoff_angle)
+        NAME(pumas_physics_property_elastic_path)
+        NAME(pumas_physics_property_transport_path)
+        NAME(pumas_physics_property_cross_section)
+        NAME(pumas_physics_element_properties)
+        NAME(pumas_physics_element_name)
+        NAME(pumas_physics_element_index)
+        NAME(pumas_physics_material_name)
+        NAME(pumas_physics_material_index)
+        NAME(pumas_physics_material_properties)
+        NAME(pumas_physics_table_value)
+        NAME(pumas_physics_table_index)
+        NAME(pumas_context_create)
+        NAME(pumas_context_random_seed_set)
+        NAME(pumas_context_random_seed_get)
+        NAME(pumas_context_transport)
+        NAME(pumas_context_transport_n)
+        NAME(pumas_b200_context_geometry_set)
+        NAME(pumas_b200_context_track_offset_set)
+        NAME(pumas_b200_context_stream_set)
+        NAME(pumas_b200_context_last_counters)
+        NAME(pumas_b200_context_last_kernel_time)
+        NAME(pumas_error_raise)
+        NAME(pumas_constant)
+#undef NAME
+        return nullptr;
+}
+
+void pumas_version(int * major, int * minor, int * patch)
+{
+        if (major != nullptr) *major = PUMAS_VERSION_MAJOR;
+        if (minor != nullptr) *minor = PUMAS_VERSION_MINOR;
+        if (patch != nullptr) *patch = PUMAS_VERSION_PATCH;
+}
+
+/* pumas.c:13673 */
+enum pumas_return pumas_constant(enum pumas_constant index, double * value)
+{
+        static const double values[PUMAS_N_CONSTANTS] = { pb::ALPHA_EM,
+                pb::AVOGADRO_NUMBER, pb::BOHR_RADIUS, pb::ELECTRON_MASS,
+                pb::ELECTRON_RADIUS, pb::HBAR_C, pb::MUON_C_TAU, pb::MUON_MASS,
+                pb::NEUTRON_MASS, pb::PION_MASS, pb::PROTON_MASS,
+                pb::TAU_C_TAU, pb::TAU_MASS };
+        if (value == nullptr)
+                return RAISE(pumas_constant, PUMAS_RETURN_VALUE_ERROR,
+                    "a NULL pointer was provided");
+        if (((int)index < 0) || (index >= PUMAS_N_CONSTANTS))
+                return RAISE(pumas_constant, PUMAS_RETURN_INDEX_ERROR,
+                    "invalid `constant' index [%d]", (int)index);
+        *value = values[index];
+        return PUMAS_RETURN_SUCCESS;
+}
+
+int pumas_b200_device_available(void) { return device_usable(nullptr); }
+
+/* ---- physics --------------------------------------------------------------- */
+enum pumas_return pumas_physics_load(
+    struct pumas_physics ** physics_ptr, FILE * stream)
+{
+        if (physics_ptr == nullptr)
+                return RAISE(pumas_physics_load, PUMAS_RETURN_PHYSICS_ERROR,
+                    "a NULL physics pointer was provided");
+        *physics_ptr = nullptr;
+        if (stream == nullptr)
+                return RAISE(pumas_physics_load, PUMAS_RETURN_PATH_ERROR,
+                    "invalid input stream (null)");
+        pumas_physics * physics = new (std::nothrow) pumas_physics;
+        if (physics == nullptr)
+                return RAISE(pumas_physics_load, PUMAS_RETURN_MEMORY_ERROR,
+                    "could not allocate memory");
+        physics->device = -1;
+        physics->d_image = nullptr;
+        std::string err;
+        const int rc = pb::load_physics_stream(stream, physics->host, err);
+        if (rc != 0) {
+                delete physics;
+                return RAISE(pumas_physics_load, (enum pumas_return)rc, "%s",
+                    err.c_str());
+        }
+        if (physics->host.view.max_components > pb::MAX_COMPONENTS) {
+                delete physics;
+                return RAISE(pumas_physics_load, PUMAS_RETURN_MEMORY_ERROR,
+                    "materials with more than %d elements are not supported",
+                    pb::MAX_COMPONENTS);
+        }
+        *physics_ptr = physics;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_dump(
+    const struct pumas_physics * physics, FILE * stream)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_dump, PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        if (stream == nullptr)
+                return RAISE(pumas_physics_dump, PUMAS_RETURN_PATH_ERROR,
+                    "invalid output stream (null)");
+        const std::vector<unsigned char> & raw = physics->host.raw;
+        if (fwrite(raw.data(), raw.size(), 1, stream) != 1)
+                return RAISE(pumas_physics_dump, PUMAS_RETURN_IO_ERROR,
+                    "could not write to dump file");
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_create(struct pumas_physics ** physics,
+    enum pumas_particle particle, const char * mdf_path,
+    const char * dedx_path, const struct pumas_physics_settings * settings)
+{
+        (void)particle;
+        (void)mdf_path;
+        (void)dedx_path;
+        (void)settings;
+        if (physics != nullptr) *physics = nullptr;
+        return RAISE(pumas_physics_create, PUMAS_RETURN_MODEL_ERROR,
+            "table generation from a MDF is not part of this library: create "
+            "the physics with the reference and load its dump with "
+            "pumas_physics_load (see INTEGRATION.md)");
+}
+
+void pumas_physics_destroy(struct pumas_physics ** physics_ptr)
+{
+        if ((physics_ptr == nullptr) || (*physics_ptr == nullptr)) return;
+        pumas_physics * physics = *physics_ptr;
+        if (physics->d_image != nullptr) cudaFree(physics->d_image);
+        delete physics;
+        *physics_ptr = nullptr;
+}
+
+double pumas_physics_cutoff(const struct pumas_physics * physics)
+{
+        return (physics == nullptr) ? -1 : physics->host.view.cutoff;
+}
+
+double pumas_physics_elastic_ratio(const struct pumas_physics * physics)
+{
+        return (physics == nullptr) ? -1 : physics->host.view.elastic_ratio;
+}
+
+enum pumas_return pumas_physics_particle(const struct pumas_physics * physics,
+    enum pumas_particle * particle, double * lifetime, double * mass)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_particle,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        const pb::Physics & p = physics->host.view;
+        if (particle != nullptr) *particle = (enum pumas_particle)p.particle;
+        if (lifetime != nullptr) *lifetime = p.ctau;
+        if (mass != nullptr) *mass = p.mass;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* Property getters, pumas.c:2854-3111. */
+#define PROPERTY_PROLOGUE(f, with_scheme)                                      \
+        *value = 0.;                                                           \
+        if (physics == nullptr)                                                \
+                return RAISE(f, PUMAS_RETURN_PHYSICS_ERROR,                    \
+                    "the Physics has not been initialised");                   \
+        const pb::Physics & p = physics->host.view;                            \
+        if (with_scheme &&                                                     \
+            (((int)scheme <= PUMAS_MODE_DISABLED) ||                           \
+                ((int)scheme >= PUMAS_MODE_STRAGGLED)))                        \
+                return RAISE(f, PUMAS_RETURN_INDEX_ERROR,                      \
+                    "invalid energy loss scheme [%d]", (int)scheme);           \
+        if ((material < 0) || (material >= p.n_materials))                     \
+                return RAISE(f, PUMAS_RETURN_INDEX_ERROR,                      \
+                    "invalid material index [%d]", material);
+
+enum pumas_return pumas_physics_property_range(
+    const struct pumas_physics * physics, enum pumas_mode scheme, int material,
+    double kinetic, double * value)
+{
+        PROPERTY_PROLOGUE(pumas_physics_property_range, 1)
+        *value = pb::cel_grammage(p, (int)scheme, material, kinetic);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_property_proper_time(
+    const struct pumas_physics * physics, enum pumas_mode scheme, int material,
+    double kinetic, double * value)
+{
+        PROPERTY_PROLOGUE(pumas_physics_property_proper_time, 1)
+        *value = pb::cel_proper_time(p, (int)scheme, material, kinetic);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_property_magnetic_rotation(
+    const struct pumas_physics * physics, int material, double kinetic,
+    double * value)
+{
+        const int scheme = 0;
+        PROPERTY_PROLOGUE(pumas_physics_property_magnetic_rotation, 0)
+        (void)scheme;
+        *value = pb::cel_magnetic_rotation(p, material, kinetic);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_property_kinetic_energy(
+    const struct pumas_physics * physics, enum pumas_mode scheme, int material,
+    double grammage, double * value)
+{
+        PROPERTY_PROLOGUE(pumas_physics_property_kinetic_energy, 1)
+        *value = pb::cel_kinetic_energy(p, (int)scheme, material, grammage);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_property_stopping_power(
+    const struct pumas_physics * physics, enum pumas_mode scheme, int material,
+    double kinetic, double * value)
+{
+        PROPERTY_PROLOGUE(pumas_physics_property_stopping_power, 1)
+        *value = pb::cel_energy_loss(p, (int)scheme, material, kinetic);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_property_energy_straggling(
+    const struct pumas_physics * physics, int material, double kinetic,
+    double * value)
+{
+        const int scheme = 0;
+        PROPERTY_PROLOGUE(pumas_physics_property_energy_straggling, 0)
+        (void)scheme;
+        *value = pb::cel_straggling(p, material, kinetic);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* pumas.c:2967-3009: cut-off angle in radians. */
+enum pumas_return pumas_physics_property_elastic_cutoff_angle(
+    const struct pumas_physics * physics, int material, double kinetic,
+    double * value)
+{
+        const int scheme = 0;
+        PROPERTY_PROLOGUE(pumas_physics_property_elastic_cutoff_angle, 0)
+        (void)scheme;
+        double mu0 = 0., invlb1 = 0.;
+        pb::table_get_msc(p, PUMAS_MODE_STRAGGLED, material, kinetic, &mu0,
+            &invlb1);
+        if (mu0 < 1E-08) {
+                *value = 2 * sqrt(mu0);
+        } else {
+                *value = acos(1. - 2 * mu0);
+        }
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_property_elastic_path(
+    const struct pumas_physics * physics, int material, double kinetic,
+    double * value)
+{
+        const int scheme = 0;
+        PROPERTY_PROLOGUE(pumas_physics_property_elastic_path, 0)
+        (void)scheme;
+        *value = pb::coulomb_ehs_length(p, material, kinetic);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* pumas.c:3050-3082: the scheme may be DISABLED here (pure elastic part). */
+enum pumas_return pumas_physics_property_transport_path(
+    const struct pumas_physics * physics, enum pumas_mode scheme, int material,
+    double kinetic, double * value)
+{
+        *value = 0.;
+        if (physics == nullptr)
+                return RAISE(pumas_physics_property_transport_path,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        const pb::Physics & p = physics->host.view;
+        if (((int)scheme < PUMAS_MODE_DISABLED) ||
+            ((int)scheme >= PUMAS_MODE_STRAGGLED))
+                return RAISE(pumas_physics_property_transport_path,
+                    PUMAS_RETURN_INDEX_ERROR,
+                    "invalid energy loss scheme [%d]", (int)scheme);
+        if ((material < 0) || (material >= p.n_materials))
+                return RAISE(pumas_physics_property_transport_path,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid material index [%d]",
+                    material);
+        double mu0 = 0., invlb1 = 0.;
+        pb::table_get_msc(p, (int)scheme, material, kinetic, &mu0, &invlb1);
+        *value = (invlb1 > 0.) ? 1. / invlb1 : DBL_MAX;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_property_cross_section(
+    const struct pumas_physics * physics, int material, double kinetic,
+    double * value)
+{
+        const int scheme = 0;
+        PROPERTY_PROLOGUE(pumas_physics_property_cross_section, 0)
+        (void)scheme;
+        *value = (kinetic < p.Kt[material]) ?
+            0. :
+            pb::del_cross_section(p, material, kinetic);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* Elements and materials, pumas.c:3270-3400. */
+int pumas_physics_element_length(const struct pumas_physics * physics)
+{
+        return (physics == nullptr) ? 0 : physics->host.view.n_elements;
+}
+
+enum pumas_return pumas_physics_element_properties(
+    const struct pumas_physics * physics, int index, double * Z, double * A,
+    double * I)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_element_properties,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        const pb::Physics & p = physics->host.view;
+        if ((index < 0) || (index >= p.n_elements))
+                return RAISE(pumas_physics_element_properties,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid element index [%d]",
+                    index);
+        if (Z != nullptr) *Z = p.element[index].Z;
+        if (A != nullptr) *A = p.element[index].A;
+        if (I != nullptr) *I = p.element[index].I;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_element_name(
+    const struct pumas_physics * physics, int index, const char ** element)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_element_name,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        if ((index < 0) || (index >= physics->host.view.n_elements))
+                return RAISE(pumas_physics_element_name,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid element index [%d]",
+                    index);
+        *element = physics->host.element_name[index].c_str();
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_element_index(
+    const struct pumas_physics * physics, const char * element, int * index)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_element_index,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        for (size_t i = 0; i < physics->host.element_name.size(); i++)
+                if (physics->host.element_name[i] == element) {
+                        *index = (int)i;
+                        return PUMAS_RETURN_SUCCESS;
+                }
+        return RAISE(pumas_physics_element_index, PUMAS_RETURN_UNKNOWN_ELEMENT,
+            "unknown element `%s'", element);
+}
+
+enum pumas_return pumas_physics_material_name(
+    const struct pumas_physics * physics, int index, const char ** material)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_material_name,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        if ((index < 0) || (index >= physics->host.view.n_materials))
+                return RAISE(pumas_physics_material_name,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid material index [%d]",
+                    index);
+        *material = physics->host.material_name[index].c_str();
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_physics_material_index(
+    const struct pumas_physics * physics, const char * material, int * index)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_material_index,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        for (size_t i = 0; i < physics->host.material_name.size(); i++)
+                if (physics->host.material_name[i] == material) {
+                        *index = (int)i;
+                        return PUMAS_RETURN_SUCCESS;
+                }
+        return RAISE(pumas_physics_material_index,
+            PUMAS_RETURN_UNKNOWN_MATERIAL, "unknown material `%s'", material);
+}
+
+int pumas_physics_material_length(const struct pumas_physics * physics)
+{
+        return (physics == nullptr) ? 0 : physics->host.view.n_materials;
+}
+
+int pumas_physics_composite_length(const struct pumas_physics * physics)
+{
+        return (physics == nullptr) ? 0 : physics->host.view.n_composites;
+}
+
+enum pumas_return pumas_physics_material_properties(
+    const struct pumas_physics * physics, int index, int * length,
+    double * density, double * I, int * components, double * fractions)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_material_properties,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        const pb::Physics & p = physics->host.view;
+        if ((index < 0) || (index >= p.n_materials))
+                return RAISE(pumas_physics_material_properties,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid material index [%d]",
+                    index);
+        if (length != nullptr) *length = p.elements_in[index];
+        if (density != nullptr) *density = p.material_density[index];
+        if (I != nullptr) *I = physics->host.material_I[index];
+        for (int i = 0; i < p.elements_in[index]; i++) {
+                const int k = p.comp_offset[index] + i;
+                if (components != nullptr) components[i] = p.comp_element[k];
+                if (fractions != nullptr) fractions[i] = p.comp_fraction[k];
+        }
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* Table rows, pumas.c:3486-3625. */
+int pumas_physics_table_length(const struct pumas_physics * physics)
+{
+        return (physics == nullptr) ? 0 : physics->host.view.n_energies;
+}
+
+enum pumas_return pumas_physics_table_value(
+    const struct pumas_physics * physics, enum pumas_property property,
+    enum pumas_mode scheme, int material, int row, double * value)
+{
+        *value = 0.;
+        if (physics == nullptr)
+                return RAISE(pumas_physics_table_value,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        const pb::Physics & p = physics->host.view;
+        if ((material < 0) || (material >= p.n_materials))
+                return RAISE(pumas_physics_table_value,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid material index [%d]",
+                    material);
+        if ((row < 0) || (row >= p.n_energies))
+                return RAISE(pumas_physics_table_value,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid `row' index [%d]", row);
+        const int s = (int)scheme;
+        const bool scheme_ok =
+            (s > PUMAS_MODE_DISABLED) && (s < PUMAS_MODE_STRAGGLED);
+        switch (property) {
+        case PUMAS_PROPERTY_KINETIC_ENERGY:
+                *value = p.K[row];
+                return PUMAS_RETURN_SUCCESS;
+        case PUMAS_PROPERTY_RANGE:
+                if (!scheme_ok) break;
+                *value = pb::col_sm(p, p.X, s, material)[row];
+                return PUMAS_RETURN_SUCCESS;
+        case PUMAS_PROPERTY_PROPER_TIME:
+                if (!scheme_ok) break;
+                *value = pb::col_sm(p, p.T, s, material)[row];
+                return PUMAS_RETURN_SUCCESS;
+        case PUMAS_PROPERTY_STOPPING_POWER:
+                if (!scheme_ok) break;
+                *value = pb::col_sm(p, p.dE, s, material)[row];
+                return PUMAS_RETURN_SUCCESS;
+        case PUMAS_PROPERTY_MAGNETIC_ROTATION:
+                *value = pb::cel_magnetic_rotation(p, material, p.K[row]);
+                return PUMAS_RETURN_SUCCESS;
+        case PUMAS_PROPERTY_CROSS_SECTION:
+                *value = pb::col_m(p, p.CS, material)[row];
+                return PUMAS_RETURN_SUCCESS;
+        default:
+                return RAISE(pumas_physics_table_value,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid `property' index [%d]",
+                    (int)property);
+        }
+        return RAISE(pumas_physics_table_value, PUMAS_RETURN_INDEX_ERROR,
+            "invalid energy loss scheme [%d]", s);
+}
+
+enum pumas_return pumas_physics_table_index(
+    const struct pumas_physics * physics, enum pumas_property property,
+    enum pumas_mode scheme, int material, double value, int * index)
+{
+        *index = 0;
+        if (physics == nullptr)
+                return RAISE(pumas_physics_table_index,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        const pb::Physics & p = physics->host.view;
+        if ((material < 0) || (material >= p.n_materials))
+                return RAISE(pumas_physics_table_index,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid material index [%d]",
+                    material);
+        const int s = (int)scheme;
+        const bool scheme_ok =
+            (s > PUMAS_MODE_DISABLED) && (s < PUMAS_MODE_STRAGGLED);
+        const double * table = nullptr;
+        if (property == PUMAS_PROPERTY_KINETIC_ENERGY)
+                table = p.K;
+        else if (property == PUMAS_PROPERTY_RANGE) {
+                if (scheme_ok) table = pb::col_sm(p, p.X, s, material);
+        } else if (property == PUMAS_PROPERTY_PROPER_TIME) {
+                if (scheme_ok) table = pb::col_sm(p, p.T, s, material);
+        } else if (property == PUMAS_PROPERTY_MAGNETIC_ROTATION) {
+                /* pumas.c:3596-3607: decreasing function of the energy. */
+                const int imax = p.n_energies - 1;
+                const double * T = pb::col_sm(p, p.T, PUMAS_MODE_CSDA, material);
+                const double factor = pb::LARMOR_FACTOR / p.mass;
+                const double t = T[imax] - value / factor;
+                if (value < 0.)
+                        return RAISE(pumas_physics_table_index,
+                            PUMAS_RETURN_VALUE_ERROR,
+                            "out of range `value' [%g]", value);
+                const int i = pb::table_index(p, T, t);
+                if ((i < 0) || (i >= imax))
+                        return RAISE(pumas_physics_table_index,
+                            PUMAS_RETURN_VALUE_ERROR,
+                            "out of range `value' [%g]", value);
+                *index = i;
+                return PUMAS_RETURN_SUCCESS;
+        } else {
+                return RAISE(pumas_physics_table_index,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid `property' index [%d]",
+                    (int)property);
+        }
+        if (table == nullptr)
+                return RAISE(pumas_physics_table_index,
+                    PUMAS_RETURN_INDEX_ERROR,
+                    "invalid energy loss scheme [%d]", s);
+        const int imax = p.n_energies - 1;
+        if (value < table[0])
+                return RAISE(pumas_physics_table_index,
+                    PUMAS_RETURN_VALUE_ERROR, "out of range `value' [%g]",
+                    value);
+        if (value == table[imax]) {
+                *index = imax;
+                return PUMAS_RETURN_SUCCESS;
+        }
+        if (value > table[imax])
+                return RAISE(pumas_physics_table_index,
+                    PUMAS_RETURN_VALUE_ERROR, "out of range `value' [%g]",
+                    value);
+        *index = pb::table_index(p, table, value);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* ---- context --------------------------------------------------------------- */
+enum pumas_return pumas_context_create(struct pumas_context ** context_,
+    const struct pumas_physics * physics, int extra_memory)
+{
+        if (context_ == nullptr)
+                return RAISE(pumas_context_create, PUMAS_RETURN_VALUE_ERROR,
+                    "a NULL context pointer was provided");
+        *context_ = nullptr;
+        if (physics == nullptr)
+                return RAISE(pumas_context_create, PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        if (extra_memory < 0) extra_memory = 0;
+        ContextImpl * c = static_cast<ContextImpl *>(
+            calloc(1, sizeof(ContextImpl) + (size_t)extra_memory + 16));
+        if (c == nullptr)
+                return RAISE(pumas_context_create, PUMAS_RETURN_MEMORY_ERROR,
+                    "could not allocate memory");
+        c->physics = physics;
+        c->extra_memory = extra_memory;
+        c->api.user_data = (extra_memory > 0) ? c->data : nullptr;
+        c->api.medium = nullptr;
+        c->api.random = nullptr;
+        c->api.recorder = nullptr;
+        /* Defaults, pumas.c:2592-2605. */
+        c->api.mode.decay =
+            (physics->host.view.particle == PUMAS_PARTICLE_MUON) ?
+            PUMAS_MODE_WEIGHTED :
+            PUMAS_MODE_RANDOMISED;
+        c->api.mode.direction = PUMAS_MODE_FORWARD;
+        c->api.mode.energy_loss = PUMAS_MODE_STRAGGLED;
+        c->api.mode.scattering = PUMAS_MODE_MIXED;
+        c->api.event = PUMAS_EVENT_NONE;
+        c->api.accuracy = 1E-02;
+        *context_ = &c->api;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+void pumas_context_destroy(struct pumas_context ** context)
+{
+        if ((context == nullptr) || (*context == nullptr)) return;
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(*context);
+        context_free_buffers(c);
+        if (c->d_status) cudaFree(c->d_status);
+        if (c->events_ready) {
+                cudaEventDestroy(c->ev0);
+                cudaEventDestroy(c->ev1);
+        }
+        free(c);
+        *context = nullptr;
+}
+
+const struct pumas_physics * pumas_context_physics_get(
+    const struct pumas_context * context)
+{
+        if (context == nullptr) return nullptr;
+        return reinterpret_cast<const ContextImpl *>(context)->physics;
+}
+
+enum pumas_return pumas_context_random_seed_set(
+    struct pumas_context * context, const unsigned long * seed_ptr)
+{
+        if (context == nullptr)
+                return RAISE(pumas_context_random_seed_set,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        if (seed_ptr == nullptr) {
+                /* pumas.c:2372-2388: seed from the OS entropy pool. */
+                unsigned long seed = 0;
+                FILE * fp = fopen("/dev/urandom", "rb");
+                if ((fp == nullptr) || (fread(&seed, sizeof seed, 1, fp) != 1)) {
+                        if (fp != nullptr) fclose(fp);
+                        return RAISE(pumas_context_random_seed_set,
+                            PUMAS_RETURN_PATH_ERROR,
+                            "could not read from `/dev/urandom'");
+                }
+                fclose(fp);
+                c->seed = seed;
+        } else {
+                c->seed = *seed_ptr;
+        }
+        c->seed_set = 1;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_context_random_seed_get(
+    struct pumas_context * context, unsigned long * seed_ptr)
+{
+        if (context == nullptr)
+                return RAISE(pumas_context_random_seed_get,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        if (!c->seed_set) {
+                const enum pumas_return rc =
+                    pumas_context_random_seed_set(context, nullptr);
+                if (rc != PUMAS_RETURN_SUCCESS) return rc;
+        }
+        *seed_ptr = c->seed;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_b200_context_geometry_set(
+    struct pumas_context * context, const struct pumas_b200_geometry * geometry)
+{
+        if ((context == nullptr) || (geometry == nullptr))
+                return RAISE(pumas_b200_context_geometry_set,
+                    PUMAS_RETURN_VALUE_ERROR, "a NULL pointer was provided");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        const pb::Physics & p = c->physics->host.view;
+        const int n_layers =
+            (geometry->kind == PUMAS_B200_GEOMETRY_UNIFORM) ? 1 :
+                                                              geometry->n_layers;
+        if ((geometry->kind != PUMAS_B200_GEOMETRY_UNIFORM) &&
+            (geometry->kind != PUMAS_B200_GEOMETRY_LAYERS))
+                return RAISE(pumas_b200_context_geometry_set,
+                    PUMAS_RETURN_MEDIUM_ERROR, "invalid geometry kind [%d]",
+                    geometry->kind);
+        if ((n_layers < 1) || (n_layers > PUMAS_B200_MAX_LAYERS))
+                return RAISE(pumas_b200_context_geometry_set,
+                    PUMAS_RETURN_MEDIUM_ERROR, "invalid number of layers [%d]",
+                    n_layers);
+        for (int i = 0; i < n_layers; i++) {
+                const int m = geometry->layer[i].material;
+                if ((m < 0) || (m >= p.n_materials))
+                        return RAISE(pumas_b200_context_geometry_set,
+                            PUMAS_RETURN_INDEX_ERROR,
+                            "invalid material index [%d]", m);
+                if ((geometry->kind == PUMAS_B200_GEOMETRY_LAYERS) &&
+                    !(geometry->z[i] < geometry->z[i + 1]))
+                        return RAISE(pumas_b200_context_geometry_set,
+                            PUMAS_RETURN_MEDIUM_ERROR,
+                            "layer boundaries must be increasing");
+                if ((geometry->layer[i].density_model ==
+                        PUMAS_B200_DENSITY_EXPONENTIAL) &&
+                    !(geometry->layer[i].scale != 0.))
+                        return RAISE(pumas_b200_context_geometry_set,
+                            PUMAS_RETURN_DENSITY_ERROR,
+                            "null scale height for layer %d", i);
+        }
+        c->geometry = *geometry;
+        c->has_geometry = 1;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_b200_context_track_offset_set(
+    struct pumas_context * context, unsigned long long offset)
+{
+        if (context == nullptr)
+                return RAISE(pumas_b200_context_track_offset_set,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        reinterpret_cast<ContextImpl *>(context)->track_offset = offset;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_b200_context_stream_set(
+    struct pumas_context * context, void * cuda_stream)
+{
+        if (context == nullptr)
+                return RAISE(pumas_b200_context_stream_set,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        reinterpret_cast<ContextImpl *>(context)->stream =
+            static_cast<cudaStream_t>(cuda_stream);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* ---- transport -------------------------------------------------------------- */
+enum pumas_return pumas_context_transport_n(struct pumas_context * context,
+    long n, struct pumas_state * states, int * events, int * media)
+{
+        if (context == nullptr)
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        if ((states == nullptr) && (n > 0))
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_VALUE_ERROR, "no state (null)");
+        if (n < 0)
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_VALUE_ERROR, "negative number of states");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        pumas_physics * physics = const_cast<pumas_physics *>(c->physics);
+        if (physics == nullptr)
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        if (!c->has_geometry)
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_MEDIUM_ERROR, "no medium specified");
+
+        /* Configuration checks, pumas.c:3152-3177. */
+        const pb::Settings cfg = settings_from(context);
+        const pb::Physics & hp = physics->host.view;
+        if ((hp.particle == PUMAS_PARTICLE_TAU) &&
+            (cfg.direction == pb::MODE_FORWARD) &&
+            (cfg.decay == pb::MODE_WEIGHTED))
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_DECAY_ERROR,
+                    "`PUMAS_MODE_WEIGHTED' mode is not valid for forward taus");
+        if ((cfg.accuracy <= 0) || (cfg.accuracy > 1))
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_ACCURACY_ERROR,
+                    "bad accuracy value (expected a value in ]0,1], got %g)",
+                    cfg.accuracy);
+        if ((cfg.direction == pb::MODE_BACKWARD) &&
+            (cfg.energy_loss > pb::MODE_CSDA) && (hp.cutoff < 1E-02))
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_ACCURACY_ERROR,
+                    "bad cutoff value for backward transport (expected a "
+                    "value greater than or equal to 0.01, got %g)",
+                    hp.cutoff);
+        if ((cfg.energy_loss < pb::MODE_DISABLED) ||
+            (cfg.energy_loss > pb::MODE_STRAGGLED))
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_INDEX_ERROR,
+                    "invalid energy loss scheme [%d]", cfg.energy_loss);
+        c->last_n = 0;
+        c->last_ms = 0.;
+        c->last_launches = 0;
+        if (n == 0) return PUMAS_RETURN_SUCCESS;
+
+        /* The device: there is no CPU path. */
+        std::string why;
+        if (!device_usable(&why))
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_INTERNAL_ERROR, "%s", why.c_str());
+        enum pumas_return rc =
+            physics_upload(FN(pumas_context_transport_n), physics);
+        if (rc != PUMAS_RETURN_SUCCESS) return rc;
+
+        if (!c->seed_set) {
+                rc = pumas_context_random_seed_set(context, nullptr);
+                if (rc != PUMAS_RETURN_SUCCESS) return rc;
+        }
+
+        cudaError_t e = context_reserve(c, n);
+        if (e != cudaSuccess)
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_MEMORY_ERROR,
+                    "could not allocate device memory (%s)",
+                    cudaGetErrorString(e));
+
+        const cudaStream_t stream = c->stream;
+        const bool states_on_device = is_device_pointer(states);
+        const bool events_on_device =
+            (events != nullptr) && is_device_pointer(events);
+        const bool media_on_device =
+            (media != nullptr) && is_device_pointer(media);
+        pb::State * d_states = states_on_device ?
+            reinterpret_cast<pb::State *>(states) :
+            c->d_states;
+        int * d_events = events_on_device ? events : c->d_events;
+        int * d_media = media_on_device ? media : c->d_media;
+
+        if (!states_on_device)
+                e = cudaMemcpyAsync(d_states, states, n * sizeof(pb::State),
+                    cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess)
+                e = cudaMemsetAsync(c->d_status, 0, sizeof(int), stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev0, stream);
+        if (e == cudaSuccess)
+                e = pb::launch_transport(physics->d_view, cfg, c->geometry,
+                    (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_states,
+                    d_events, d_media, c->d_status, c->d_random, c->d_steps,
+                    stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev1, stream);
+        int status = 0;
+        if ((e == cudaSuccess) && !states_on_device)
+                e = cudaMemcpyAsync(states, d_states, n * sizeof(pb::State),
+                    cudaMemcpyDeviceToHost, stream);
+        if ((e == cudaSuccess) && (events != nullptr) && !events_on_device)
+                e = cudaMemcpyAsync(events, d_events, n * sizeof(int),
+                    cudaMemcpyDeviceToHost, stream);
+        if ((e == cudaSuccess) && (media != nullptr) && !media_on_device)
+                e = cudaMemcpyAsync(media, d_media, 2 * n * sizeof(int),
+                    cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess)
+                e = cudaMemcpyAsync(&status, c->d_status, sizeof(int),
+                    cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess)
+                return RAISE(pumas_context_transport_n,
+                    PUMAS_RETURN_INTERNAL_ERROR, "CUDA error (%s)",
+                    cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->last_ms = ms;
+        c->last_launches = 1;
+        c->last_n = n;
+        c->track_offset += (unsigned long long)n;
+
+        if (status != 0)
+                return RAISE(pumas_context_transport_n,
+                    (enum pumas_return)status, "%s", return_text(status));
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_context_transport(struct pumas_context * context,
+    struct pumas_state * state, enum pumas_event * event,
+    struct pumas_medium * media[2])
+{
+        if (context == nullptr)
+                return RAISE(pumas_context_transport, PUMAS_RETURN_VALUE_ERROR,
+                    "no context (null)");
+        if (state == nullptr)
+                return RAISE(pumas_context_transport, PUMAS_RETURN_VALUE_ERROR,
+                    "no state (null)");
+        if (media != nullptr) media[0] = media[1] = nullptr;
+        int e = PUMAS_EVENT_NONE;
+        const enum pumas_return rc =
+            pumas_context_transport_n(context, 1, state, &e, nullptr);
+        if (event != nullptr) *event = (enum pumas_event)e;
+        return rc;
+}
+
+enum pumas_return pumas_b200_context_last_counters(
+    struct pumas_context * context, long n, unsigned int * n_random,
+    unsigned int * n_steps)
+{
+        if (context == nullptr)
+                return RAISE(pumas_b200_context_last_counters,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        if ((n < 0) || (n > c->last_n))
+                return RAISE(pumas_b200_context_last_counters,
+                    PUMAS_RETURN_VALUE_ERROR,
+                    "the last batch held %ld tracks, %ld requested", c->last_n,
+                    n);
+        cudaError_t e = cudaSuccess;
+        if (n_random != nullptr)
+                e = cudaMemcpy(n_random, c->d_random, n * sizeof(unsigned int),
+                    cudaMemcpyDeviceToHost);
+        if ((e == cudaSuccess) && (n_steps != nullptr))
+                e = cudaMemcpy(n_steps, c->d_steps, n * sizeof(unsigned int),
+                    cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess)
+                return RAISE(pumas_b200_context_last_counters,
+                    PUMAS_RETURN_INTERNAL_ERROR, "CUDA error (%s)",
+                    cudaGetErrorString(e));
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_b200_context_last_kernel_time(
+    struct pumas_context * context, double * milliseconds, int * launches)
+{
+        if (context == nullptr)
+                return RAISE(pumas_b200_context_last_kernel_time,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        if (milliseconds != nullptr) *milliseconds = c->last_ms;
+        if (launches != nullptr) *launches = c->last_launches;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+} /* extern "C" */

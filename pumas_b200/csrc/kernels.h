@@ -1,0 +1,26 @@
+/*
+ * kernels.h -- host interface of the transport kernels (kernels.cu).
+ */
+#ifndef PB_KERNELS_H
+#define PB_KERNELS_H
+
+#include <cuda_runtime.h>
+
+#include "pb_media.h"
+#include "pb_physics.h"
+
+namespace pb {
+
+constexpr int TRANSPORT_BLOCK = 128;
+
+/* Transport n tracks, one thread each. All pointers are device pointers;
+ * `status` receives the first non-zero pumas_return raised by a track. Track i
+ * draws from the Philox stream (seed, offset + i). */
+cudaError_t launch_transport(const Physics & p, const Settings & cfg,
+    const Geometry & geo, uint64_t seed, uint64_t offset, long n,
+    State * states, int * events, int * media, int * status,
+    unsigned int * n_random, unsigned int * n_steps, cudaStream_t stream);
+
+} /* namespace pb */
+
+#endif

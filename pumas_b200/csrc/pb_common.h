@@ -18,7 +18,7 @@
 
 #if defined(__CUDACC__)
 #define PB_FN __host__ __device__ __forceinline__
-#define PB_NOINLINE __host__ __device__ __noinline__
+#define PB_NOINLINE inline __host__ __device__ __noinline__
 #else
 #define PB_FN inline
 #define PB_NOINLINE inline
@@ -30,6 +30,8 @@ namespace pb {
 constexpr int N_SCHEMES = 2;
 constexpr int N_LARMOR_ORDERS = 8;
 constexpr int N_DEL_PROCESSES = 4;
+/* Largest number of elements per material the hard elastic event handles. */
+constexpr int MAX_COMPONENTS = 8;
 constexpr double BMC_ALPHA = 2.0;
 constexpr double EPSILON_X = 3E-03;
 constexpr double STEP_MIN = 1E-07;

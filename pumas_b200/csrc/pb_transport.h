@@ -29,7 +29,7 @@
 
 namespace pb {
 
-constexpr int MAX_COMPONENTS = 8; /* elements per material handled by do_ehs */
+
 
 /* Working precision of the Coulomb pole reduction (see pb_coulomb.h). */
 #if defined(__CUDA_ARCH__) || defined(PB_FORCE_DD)

@@ -15,106 +15,22 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-# ---- enums (include/pumas_b200.h) -----------------------------------------
-MODE_DISABLED, MODE_CSDA, MODE_MIXED, MODE_STRAGGLED = -1, 0, 1, 2
-MODE_WEIGHTED, MODE_RANDOMISED = 0, 1
-MODE_FORWARD, MODE_BACKWARD = 0, 1
-EVENT_NONE = 0
-EVENT_LIMIT_ENERGY, EVENT_LIMIT_DISTANCE = 1, 2
-EVENT_LIMIT_GRAMMAGE, EVENT_LIMIT_TIME = 4, 8
-EVENT_MEDIUM = 16
-EVENT_VERTEX_DEL, EVENT_VERTEX_COULOMB, EVENT_VERTEX_DECAY = 480, 512, 1024
-EVENT_WEIGHT = 2048
-STEP_CHECK, STEP_RAW = 0, 1
-GEOMETRY_UNIFORM, GEOMETRY_LAYERS = 0, 1
-DENSITY_CONSTANT, DENSITY_EXPONENTIAL = 0, 1
-MAX_LAYERS = 8
+import sys
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
-# struct pumas_state (pumas.h:289-309): 104 bytes.
-STATE_DTYPE = np.dtype([
-    ("charge", "f8"), ("energy", "f8"), ("distance", "f8"), ("grammage", "f8"),
-    ("time", "f8"), ("weight", "f8"), ("position", "f8", 3),
-    ("direction", "f8", 3), ("decayed", "i4"), ("_pad", "i4")])
-assert STATE_DTYPE.itemsize == 104
+from pumas_b200 import (  # noqa: E402,F401
+    DENSITY_CONSTANT, DENSITY_EXPONENTIAL, EVENT_LIMIT_DISTANCE,
+    EVENT_LIMIT_ENERGY, EVENT_LIMIT_GRAMMAGE, EVENT_LIMIT_TIME, EVENT_MEDIUM,
+    EVENT_NONE, EVENT_VERTEX_COULOMB, EVENT_VERTEX_DECAY, EVENT_VERTEX_DEL,
+    EVENT_WEIGHT, GEOMETRY_LAYERS, GEOMETRY_UNIFORM, MAX_LAYERS, MODE_BACKWARD,
+    MODE_CSDA, MODE_DISABLED, MODE_FORWARD, MODE_MIXED, MODE_RANDOMISED,
+    MODE_STRAGGLED, MODE_WEIGHTED, STATE_DTYPE, STEP_CHECK, STEP_RAW, Geometry,
+    Layer, layered_geometry, make_states, uniform_geometry)
+from pumas_b200 import ContextStruct as Context  # noqa: E402
+
 STATE_FIELDS = ("charge", "energy", "distance", "grammage", "time", "weight",
                 "position", "direction")
-
-
-class ContextMode(ctypes.Structure):
-    _fields_ = [("energy_loss", ctypes.c_int), ("decay", ctypes.c_int),
-                ("direction", ctypes.c_int), ("scattering", ctypes.c_int)]
-
-
-class ContextLimit(ctypes.Structure):
-    _fields_ = [("energy", ctypes.c_double), ("distance", ctypes.c_double),
-                ("grammage", ctypes.c_double), ("time", ctypes.c_double)]
-
-
-class Context(ctypes.Structure):
-    """struct pumas_context (pumas.h:636-672)."""
-    _fields_ = [("medium", ctypes.c_void_p), ("random", ctypes.c_void_p),
-                ("recorder", ctypes.c_void_p), ("user_data", ctypes.c_void_p),
-                ("mode", ContextMode), ("event", ctypes.c_int),
-                ("limit", ContextLimit), ("accuracy", ctypes.c_double)]
-
-
-class Layer(ctypes.Structure):
-    _fields_ = [("material", ctypes.c_int), ("has_locals", ctypes.c_int),
-                ("density_model", ctypes.c_int), ("reserved", ctypes.c_int),
-                ("density", ctypes.c_double), ("scale", ctypes.c_double),
-                ("eps", ctypes.c_double), ("magnet", ctypes.c_double * 3)]
-
-
-class Geometry(ctypes.Structure):
-    """struct pumas_b200_geometry (include/pumas_b200_geometry.h)."""
-    _fields_ = [("kind", ctypes.c_int), ("n_layers", ctypes.c_int),
-                ("step_type", ctypes.c_int), ("reserved", ctypes.c_int),
-                ("step_default", ctypes.c_double),
-                ("step_epsilon", ctypes.c_double),
-                ("z", ctypes.c_double * (MAX_LAYERS + 1)),
-                ("layer", Layer * MAX_LAYERS)]
-
-
-def uniform_geometry(material, density=None):
-    """One infinite medium (examples/pumas/straight.c:61-74)."""
-    g = Geometry()
-    g.kind = GEOMETRY_UNIFORM
-    g.n_layers = 1
-    g.step_type = STEP_CHECK
-    g.step_default = 1e3
-    g.step_epsilon = 1e-7
-    g.layer[0].material = material
-    if density is not None:
-        g.layer[0].has_locals = 1
-        g.layer[0].density = density
-    return g
-
-
-def layered_geometry(z, layers, step_type=STEP_RAW):
-    """Stack of horizontal layers (examples/pumas/geometry.c:104-163).
-    layers: list of dicts(material, density=None, scale=None, eps=0.05,
-    magnet=(0, 0, 0))."""
-    assert len(z) == len(layers) + 1 <= MAX_LAYERS + 1
-    g = Geometry()
-    g.kind = GEOMETRY_LAYERS
-    g.n_layers = len(layers)
-    g.step_type = step_type
-    g.step_default = 1e3
-    g.step_epsilon = 1e-7
-    for i, zi in enumerate(z):
-        g.z[i] = zi
-    for i, l in enumerate(layers):
-        g.layer[i].material = l["material"]
-        if l.get("density") is not None:
-            g.layer[i].has_locals = 1
-            g.layer[i].density = l["density"]
-            if l.get("scale") is not None:
-                g.layer[i].density_model = DENSITY_EXPONENTIAL
-                g.layer[i].scale = l["scale"]
-                g.layer[i].eps = l.get("eps", 0.05)
-            for k, b in enumerate(l.get("magnet", (0., 0., 0.))):
-                g.layer[i].magnet[k] = b
-    return g
 
 
 def make_settings(energy_loss=MODE_STRAGGLED, scattering=MODE_MIXED,
@@ -133,17 +49,6 @@ def make_settings(energy_loss=MODE_STRAGGLED, scattering=MODE_MIXED,
     c.limit.time = limit_time
     c.accuracy = accuracy
     return c
-
-
-def make_states(n, energy, charge=-1., direction=(0., 0., 1.), weight=1.,
-                position=(0., 0., 0.)):
-    s = np.zeros(n, dtype=STATE_DTYPE)
-    s["charge"] = charge
-    s["energy"] = energy
-    s["weight"] = weight
-    s["direction"] = np.asarray(direction, dtype="f8")
-    s["position"] = np.asarray(position, dtype="f8")
-    return s
 
 
 # ---- fixtures ---------------------------------------------------------------

@@ -1,0 +1,140 @@
+"""GPU parity: the CUDA path, called through the C ABI
+(pumas_context_transport_n), against the reference itself (oracle/_ref) on the
+same seeded inputs and the same Philox streams.
+
+Criterion (BASELINE.json north_star): per-track final states agree within 1e-9
+relative in fp64; the fraction of tracks whose event sequence diverges (a
+different number of consumed variates or a different end event) is reported and
+must stay small, since the two sides use different libm implementations
+(glibc vs CUDA: <= 2 ulp apart) whose differences can flip a comparison
+against a random number.
+"""
+import numpy as np
+import pytest
+
+import harness
+import pumas_b200 as pb
+from workloads import WORKLOADS
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9
+N_TRACKS = {
+    "headline": 3000, "rock_3km": 1500, "straight": 4000,
+    "straight_mixed": 4000, "csda_water": 20000, "csda_spectrum_fwd": 20000,
+    "csda_spectrum_bwd": 20000, "mixed_loss": 20000,
+    "mixed_loss_scattering": 2000, "mixed_loss_bwd": 4000,
+    "geometry_detailed": 4000, "geometry_fast": 20000, "layers_check": 2000,
+    "decay_randomised": 2000, "no_loss": 1500, "tau_ice": 20000,
+}
+# Largest tolerated fraction of tracks whose event sequence diverges.
+MAX_DIVERGED = 2e-3
+
+_cache = {}
+
+
+def _sides(dump):
+    if dump not in _cache:
+        if not harness.have_oracle():
+            pytest.skip("oracle/_ref not built")
+        physics = pb.Physics(harness.dump_path(dump))
+        _cache[dump] = (harness.Oracle(dump), physics)
+    return _cache[dump]
+
+
+def run_gpu(physics, w, seed=0, offset=0):
+    ctx = pb.Context(physics, seed=seed)
+    ctx.configure(w["settings"])
+    ctx.geometry(w["geometry"])
+    ctx.track_offset(offset)
+    states = w["states"].copy()
+    events, media = ctx.transport(states)
+    nrand, nsteps = ctx.last_counters(len(states))
+    return states, events, media, nrand, nsteps
+
+
+@pytest.mark.parametrize("name", sorted(WORKLOADS))
+def test_parity(name):
+    assert pb.device_available(), "no B200 visible: the GPU tests need one"
+    dump, builder, kwargs = WORKLOADS[name]
+    oracle, physics = _sides(dump)
+    n = N_TRACKS[name]
+    w = builder(oracle.material, n, **kwargs)
+    import os
+    so, eo, mo, ro, rc, _ = oracle.transport(
+        w["settings"], w["geometry"], w["states"], seed=7, offset=1000,
+        threads=os.cpu_count() or 1)
+    assert rc == 0
+    sg, eg, mg, rg, steps = run_gpu(physics, w, seed=7, offset=1000)
+    c = harness.compare_states(so, sg, eo, eg, ro, rg, rtol=RTOL)
+    frac = c["n_diverged"] / c["n"]
+    print("\n%s: n=%d match=%d bitexact=%d diverged=%d (%.2e) max_rel=%.3g "
+          "steps/track=%.1f" % (name, c["n"], c["n_match"], c["n_bitexact"],
+                                c["n_diverged"], frac, c["max_rel"],
+                                steps.mean()))
+    assert frac <= MAX_DIVERGED
+    # every track whose event sequence stayed in sync agrees within 1e-9
+    assert c["n_match"] == c["n"] - c["n_diverged"], c["max_rel"]
+    sync = ~c["diverged"]
+    assert (mo[sync] == mg[sync]).all()
+
+
+def test_device_pointers_and_offsets():
+    """States resident in HBM (torch tensors), two half batches with explicit
+    track offsets == one full batch."""
+    import torch
+    oracle, physics = _sides("materials.muon")
+    dump, builder, kwargs = WORKLOADS["straight"]
+    n = 2048
+    w = builder(oracle.material, n, **kwargs)
+    full, _, _, _, _ = run_gpu(physics, w, seed=3, offset=0)
+
+    ctx = pb.Context(physics, seed=3)
+    ctx.configure(w["settings"])
+    ctx.geometry(w["geometry"])
+    host = torch.from_numpy(w["states"].copy().view(np.uint8).reshape(n, 104))
+    dev = host.cuda()
+    events = torch.zeros(n, dtype=torch.int32, device="cuda")
+    half = n // 2
+    ctx.stream(torch.cuda.current_stream().cuda_stream)
+    ctx.track_offset(half)
+    ctx.transport_device(half, dev[half:].data_ptr(), events[half:].data_ptr())
+    ctx.track_offset(0)
+    ctx.transport_device(half, dev.data_ptr(), events.data_ptr())
+    torch.cuda.synchronize()
+    out = dev.cpu().numpy().reshape(-1).view(pb.STATE_DTYPE)
+    for f in harness.STATE_FIELDS:
+        assert np.array_equal(out[f], full[f]), f
+    assert (events.cpu().numpy() == pb.EVENT_LIMIT_DISTANCE).all()
+
+
+def test_error_paths():
+    oracle, physics = _sides("materials.muon")
+    ctx = pb.Context(physics)
+    s = pb.make_states(4, 1.)
+    with pytest.raises(pb.PumasError) as e:  # no medium
+        ctx.transport(s)
+    assert e.value.rc == 12
+    ctx.geometry(pb.uniform_geometry(0))
+    s["direction"][2] = [0.5, 0., 0.]  # pumas.c:3144
+    with pytest.raises(pb.PumasError) as e:
+        ctx.transport(s)
+    assert e.value.rc == 5
+    s = pb.make_states(4, 1.)
+    ctx.api.accuracy = 2.  # pumas.c:3164
+    with pytest.raises(pb.PumasError) as e:
+        ctx.transport(s)
+    assert e.value.rc == 1
+    ctx.api.accuracy = 1e-2
+    ctx.api.mode.energy_loss = pb.MODE_DISABLED  # pumas.c:3226
+    ctx.api.mode.scattering = pb.MODE_DISABLED
+    with pytest.raises(pb.PumasError) as e:
+        ctx.transport(s)
+    assert e.value.rc == 15
+    # decayed state: nothing to do, VERTEX_DECAY (pumas.c:3135)
+    ctx.api.mode.energy_loss = pb.MODE_CSDA
+    ctx.api.event = pb.EVENT_LIMIT_DISTANCE
+    ctx.api.limit.distance = 10.
+    s["decayed"] = 1
+    events, _ = ctx.transport(s)
+    assert (events == pb.EVENT_VERTEX_DECAY).all()

@@ -1,0 +1,207 @@
+"""The workloads of BASELINE.json / SURVEY.md section 8(d), as concrete inputs
+shared by the CPU (port) and GPU parity tests and by bench.py.
+
+Each workload is a function (physics_material_index) -> dict(settings,
+geometry, states) for n tracks. Initial states are deterministic functions of
+(n, seed) drawn with numpy, so every implementation gets the same inputs."""
+import numpy as np
+
+from harness import (EVENT_LIMIT_DISTANCE, EVENT_LIMIT_ENERGY,
+                     EVENT_LIMIT_GRAMMAGE, EVENT_LIMIT_TIME, MODE_BACKWARD,
+                     MODE_CSDA, MODE_DISABLED, MODE_FORWARD, MODE_MIXED,
+                     MODE_RANDOMISED, MODE_STRAGGLED, MODE_WEIGHTED, STEP_CHECK,
+                     STEP_RAW, layered_geometry, make_settings, make_states,
+                     uniform_geometry)
+
+
+def log_uniform(n, lo, hi, seed):
+    rng = np.random.default_rng(seed)
+    return np.exp(rng.uniform(np.log(lo), np.log(hi), n))
+
+
+def isotropic(n, seed):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, n)
+    phi = rng.uniform(0, 2 * np.pi, n)
+    s = np.sqrt(1 - c * c)
+    return np.stack([s * np.cos(phi), s * np.sin(phi), c], axis=1)
+
+
+def headline(material, n, seed=0):
+    """Forward, straggled, mixed scattering, 1 km standard rock, 1 TeV."""
+    return dict(
+        settings=make_settings(MODE_STRAGGLED, MODE_MIXED,
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=1e3),
+        geometry=uniform_geometry(material("StandardRock")),
+        states=make_states(n, 1e3))
+
+
+def straight(material, n, seed=0, scattering=MODE_DISABLED, spectrum=False):
+    """configs[0], examples/pumas/straight.c:110-153: backward, straggled,
+    1 km standard rock, elevation 90 deg, final energy 1 GeV (or log-uniform
+    1 GeV .. 1 TeV), random charge."""
+    rng = np.random.default_rng(seed)
+    if spectrum:
+        kf = log_uniform(n, 1., 1e3, seed + 1)
+        wf = kf * np.log(1e3) * 2
+    else:
+        kf = 1.
+        wf = 2.
+    charge = np.where(rng.uniform(size=n) > 0.5, 1., -1.)
+    return dict(
+        settings=make_settings(MODE_STRAGGLED, scattering,
+                               direction=MODE_BACKWARD,
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=1e3),
+        geometry=uniform_geometry(material("StandardRock")),
+        states=make_states(n, kf, charge=charge, weight=wf,
+                           direction=(0., 0., -1.)))
+
+
+def csda_water(material, n, seed=0):
+    """configs[1]: forward CSDA, no scattering, 1 TeV muons through 1 km of
+    water (closed form path, pumas.c:4777)."""
+    return dict(
+        settings=make_settings(MODE_CSDA, MODE_DISABLED,
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=1e3),
+        geometry=uniform_geometry(material("Water")),
+        states=make_states(n, 1e3))
+
+
+def csda_spectrum(material, n, seed=0, direction=MODE_FORWARD):
+    """Closed form CSDA over 10 decades of energy with every limit armed."""
+    return dict(
+        settings=make_settings(
+            MODE_CSDA, MODE_DISABLED, direction=direction,
+            event=(EVENT_LIMIT_DISTANCE | EVENT_LIMIT_GRAMMAGE |
+                   EVENT_LIMIT_ENERGY | EVENT_LIMIT_TIME),
+            limit_distance=300., limit_grammage=5e5,
+            limit_energy=(1e-2 if direction == MODE_FORWARD else 1e5),
+            limit_time=250.),
+        geometry=uniform_geometry(material("StandardRock")),
+        states=make_states(n, log_uniform(n, 1e-3, 1e7, seed),
+                           direction=isotropic(n, seed + 1)))
+
+
+def rock_3km(material, n, seed=0, energy=1e4):
+    """configs[2]: forward, straggled, mixed scattering, 3 km standard rock."""
+    return dict(
+        settings=make_settings(MODE_STRAGGLED, MODE_MIXED,
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=3e3),
+        geometry=uniform_geometry(material("StandardRock")),
+        states=make_states(n, energy))
+
+
+def mixed_loss(material, n, seed=0, scattering=MODE_DISABLED,
+               direction=MODE_FORWARD):
+    """Mixed (hybrid) energy loss, pumas.c:5632-5695."""
+    e = 1e3 if direction == MODE_FORWARD else 10.
+    return dict(
+        settings=make_settings(MODE_MIXED, scattering, direction=direction,
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=1e3),
+        geometry=uniform_geometry(material("StandardRock")),
+        states=make_states(n, e, direction=(0., 0., 1.)))
+
+
+def geometry_example(material, n, seed=0, phase="detailed", thickness=100.,
+                     elevation=60.):
+    """configs[3], examples/pumas/geometry.c: rock [0, t) + exponential air
+    [t, 1000) with a geomagnetic field, backward, energy limit.
+    phase "detailed": Kf = 1 GeV, straggled + mixed up to 100 GeV
+    (geometry.c:268-277); phase "fast": Kf = 100 GeV, mixed loss, no scattering
+    up to 1e6 GeV (geometry.c:278-286)."""
+    geo = layered_geometry(
+        [0., thickness, 1e3],
+        [dict(material=material("StandardRock"), density=2.65e3),
+         dict(material=material("Air"), density=1.205, scale=12e3, eps=5e-2,
+              magnet=(0., 2e-5, -4e-5))],
+        step_type=STEP_RAW)
+    c = np.cos(np.radians(90. - elevation))
+    s = np.sqrt(1. - c * c)
+    rng = np.random.default_rng(seed)
+    charge = np.where(rng.uniform(size=n) > 0.5, 1., -1.)
+    if phase == "detailed":
+        settings = make_settings(MODE_STRAGGLED, MODE_MIXED,
+                                 direction=MODE_BACKWARD,
+                                 event=EVENT_LIMIT_ENERGY, limit_energy=1e2)
+        kf = 1.
+    else:
+        settings = make_settings(MODE_MIXED, MODE_DISABLED,
+                                 direction=MODE_BACKWARD,
+                                 event=EVENT_LIMIT_ENERGY, limit_energy=1e6)
+        kf = 1e2
+    return dict(settings=settings, geometry=geo,
+                states=make_states(n, kf, charge=charge, weight=2.,
+                                   direction=(-s, 0., -c)))
+
+
+def layers_check(material, n, seed=0):
+    """Three layers with exact boundary location (PUMAS_STEP_CHECK bisection,
+    pumas.c:6424-6485), forward, isotropic directions, starting mid-stack."""
+    geo = layered_geometry(
+        [-50., 0., 30., 80.],
+        [dict(material=material("Water")),
+         dict(material=material("StandardRock")),
+         dict(material=material("Water"), density=1.03e3)],
+        step_type=STEP_CHECK)
+    return dict(
+        settings=make_settings(MODE_STRAGGLED, MODE_MIXED),
+        geometry=geo,
+        states=make_states(n, log_uniform(n, 0.5, 50., seed),
+                           direction=isotropic(n, seed + 1),
+                           position=(0., 0., 10.)))
+
+
+def decay_randomised(material, n, seed=0):
+    """Randomised decay + time limit in the stepping engine."""
+    return dict(
+        settings=make_settings(MODE_STRAGGLED, MODE_MIXED,
+                               decay=MODE_RANDOMISED,
+                               event=EVENT_LIMIT_TIME, limit_time=2e3),
+        geometry=uniform_geometry(material("Water")),
+        states=make_states(n, log_uniform(n, 0.2, 20., seed)))
+
+
+def no_loss(material, n, seed=0):
+    """Energy loss disabled, scattering only (pumas.c:5611-5625)."""
+    return dict(
+        settings=make_settings(MODE_DISABLED, MODE_MIXED,
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=50.),
+        geometry=uniform_geometry(material("StandardRock")),
+        states=make_states(n, log_uniform(n, 0.1, 1e3, seed)))
+
+
+def tau_ice(material, n, seed=0):
+    """configs[4]: tau, backward, straggled, weighted decay, ice
+    (dump ice.tau)."""
+    return dict(
+        settings=make_settings(MODE_STRAGGLED, MODE_MIXED,
+                               direction=MODE_BACKWARD, decay=MODE_WEIGHTED,
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=10.),
+        geometry=uniform_geometry(material("Ice")),
+        states=make_states(n, log_uniform(n, 1e2, 1e6, seed), weight=1.,
+                           direction=(0., 0., -1.)))
+
+
+# name -> (dump, builder, kwargs)
+WORKLOADS = {
+    "headline": ("materials.muon", headline, {}),
+    "straight": ("materials.muon", straight, {}),
+    "straight_mixed": ("materials.muon", straight,
+                       dict(scattering=MODE_MIXED, spectrum=True)),
+    "csda_water": ("materials.muon", csda_water, {}),
+    "csda_spectrum_fwd": ("materials.muon", csda_spectrum, {}),
+    "csda_spectrum_bwd": ("materials.muon", csda_spectrum,
+                          dict(direction=MODE_BACKWARD)),
+    "rock_3km": ("materials.muon", rock_3km, {}),
+    "mixed_loss": ("materials.muon", mixed_loss, {}),
+    "mixed_loss_scattering": ("materials.muon", mixed_loss,
+                              dict(scattering=MODE_MIXED)),
+    "mixed_loss_bwd": ("materials.muon", mixed_loss,
+                       dict(direction=MODE_BACKWARD, scattering=MODE_MIXED)),
+    "geometry_detailed": ("materials.muon", geometry_example, {}),
+    "geometry_fast": ("materials.muon", geometry_example, dict(phase="fast")),
+    "layers_check": ("materials.muon", layers_check, {}),
+    "decay_randomised": ("materials.muon", decay_randomised, {}),
+    "no_loss": ("materials.muon", no_loss, {}),
+    "tau_ice": ("ice.tau", tau_ice, {}),
+}
