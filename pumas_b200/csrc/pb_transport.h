@@ -1000,152 +1000,45 @@ PB_FN int straight_flag(
             0;
 }
 
-/* pumas.c:5194-5514 */
-template <class Rng>
-PB_FN int transport_with_stepping(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Track & trk, Rng & rng, State & state,
-    int * medium_ptr, Locals & locals, double step_max_medium,
-    int step_max_type, double step_max_locals)
-{
-        int medium = *medium_ptr;
-        int material = geo.layer[medium].material;
+/*
+ * transport_with_stepping (pumas.c:5194-5514) as a resumable state machine.
+ *
+ * The reference runs one track to completion inside nested loops. Here the
+ * loop is cut at the points where a track needs a different kind of work, so
+ * that a GPU scheduler can regroup tracks by pending work (kernels.cu):
+ *   stepping_begin   the prologue up to the first transport_limit (:5210-5273)
+ *   stepping_step    one loop iteration up to the event dispatch (:5277-5335,
+ *                    medium changes :5417-5467 handled in place)
+ *   stepping_del     a hard inelastic event, transport_do_del (:5340-5392)
+ *   stepping_ehs     a hard elastic event, transport_do_ehs (:5393-5402)
+ *   stepping_rearm   re-arm after an event (:5404-5416, :5476-5488)
+ *   stepping_finish  final protections (:5492-5513)
+ * `Loop` holds the locals of the reference function that live across steps.
+ * The CPU build and the simple kernel just chain the pieces (transport_track).
+ */
+enum Phase {
+        PHASE_STEP = 0, /* needs a Monte Carlo step */
+        PHASE_EHS = 1,  /* pending hard elastic event */
+        PHASE_DEL = 2,  /* pending hard inelastic event */
+        PHASE_DONE = 3  /* transport over, trk.step_event is the end event */
+};
 
-        const int scheme = cfg.energy_loss;
-        int straight = straight_flag(cfg, step_max_locals, locals);
-
-        trk.step_event = EVENT_NONE;
-
-        double ti = state.time;
-        double wi = state.weight;
-        double Xi = state.grammage;
-        double dei, Xf;
-        if (scheme > MODE_DISABLED) {
-                const double ki = state.energy;
-                Xf = cel_grammage(p, scheme, material, ki);
-                dei = 1. / cel_energy_loss(p, scheme, material, ki);
-        } else {
-                Xf = dei = 0.;
-        }
-
-        if ((cfg.event & EVENT_LIMIT_DISTANCE) &&
-            (state.distance >= cfg.limit_distance))
-                return EVENT_LIMIT_DISTANCE;
-        if ((cfg.event & EVENT_LIMIT_GRAMMAGE) &&
-            (state.grammage >= cfg.limit_grammage))
-                return EVENT_LIMIT_GRAMMAGE;
-        if ((cfg.event & EVENT_LIMIT_TIME) && (state.time >= cfg.limit_time))
-                return EVENT_LIMIT_TIME;
-        if (state.weight <= 0.) return EVENT_WEIGHT;
-
+struct Loop {
+        int medium;
+        int material;
+        int straight;
+        int step_max_type;
+        int first; /* step_index == 1 */
+        double ti, wi, Xi, Xf, dei;
         double grammage_max;
-        trk.step_event = EVENT_NONE;
-        trk.step_first = 1;
-        trk.step_X_limit = (cfg.event & EVENT_LIMIT_ENERGY) ?
-            cel_grammage(p, (scheme > MODE_DISABLED) ? scheme : MODE_CSDA,
-                material, cfg.limit_energy) :
-            0.;
-        trk.step_invlb1 = 0;
-        transport_limit(p, cfg, trk, rng, state, material, Xi, Xf, &grammage_max);
-        if (trk.step_event) return trk.step_event;
+        double step_max_medium;
+        double step_max_locals;
+        Locals locals;
+};
 
-        int step_index = 1;
-        for (;;) {
-                if (step_index > 1) {
-                        step_max_type = medium_locate(geo, cfg.direction, state,
-                            false, 0, true, &step_max_medium);
-                        if ((step_max_medium > 0.) &&
-                            (step_max_type == STEP_CHECK))
-                                step_max_medium += 0.5 * STEP_MIN;
-                }
-
-                int new_medium = -1;
-                if (!step_transport(p, cfg, geo, trk, rng, state, straight,
-                        medium, locals, grammage_max, step_max_medium,
-                        step_max_type, &step_max_locals, &new_medium))
-                        return trk.step_event;
-                step_index++;
-
-                if (!trk.step_event) continue;
-
-                /* Weight update at a boundary or hard loss. */
-                if ((cfg.direction == MODE_BACKWARD) &&
-                    (cfg.energy_loss >= MODE_CSDA)) {
-                        const double wt = (cfg.decay == MODE_WEIGHTED) ?
-                            exp(-fabs(state.time - ti) / p.ctau) :
-                            1.;
-                        state.weight = wi * wt * dei *
-                            cel_energy_loss(p, scheme, material, state.energy);
-                } else if (cfg.decay == MODE_WEIGHTED) {
-                        state.weight =
-                            wi * exp(-fabs(state.time - ti) / p.ctau);
-                }
-
-                if (trk.step_event &
-                    (EVENT_LIMIT | EVENT_WEIGHT | EVENT_VERTEX_DECAY)) {
-                        break;
-                } else if (trk.step_event &
-                    (EVENT_VERTEX_DEL | EVENT_VERTEX_COULOMB)) {
-                        if (trk.step_event & EVENT_VERTEX_DEL) {
-                                transport_do_del(
-                                    p, cfg, trk, rng, state, material);
-                                if ((cfg.event & trk.step_event) ||
-                                    trk.step_event == EVENT_WEIGHT)
-                                        break;
-                                trk.step_first = 1;
-                                trk.step_invlb1 = 0;
-                        } else {
-                                transport_do_ehs(p, cfg, rng, state, material);
-                                if (cfg.event & trk.step_event) break;
-                        }
-
-                        if (step_max_locals > 0.) {
-                                step_max_locals = set_locals(p, geo,
-                                    cfg.accuracy, medium, state, &locals);
-                                if (locals.density <= 0.) {
-                                        trk.error = RETURN_DENSITY_ERROR;
-                                        return trk.step_event;
-                                }
-                        }
-                } else if (trk.step_event & EVENT_MEDIUM) {
-                        medium = new_medium;
-                        if ((medium < 0) || (cfg.event & EVENT_MEDIUM)) break;
-                        material = geo.layer[medium].material;
-                        locals.density = 0.;
-                        locals.magnet[0] = locals.magnet[1] =
-                            locals.magnet[2] = 0.;
-                        locals.magnetized = 0;
-                        step_max_locals = set_locals(
-                            p, geo, cfg.accuracy, medium, state, &locals);
-                        if (locals.density <= 0.) {
-                                trk.error = RETURN_DENSITY_ERROR;
-                                return trk.step_event;
-                        }
-                        straight = straight_flag(cfg, step_max_locals, locals);
-
-                        const int tmp_scheme =
-                            scheme > MODE_DISABLED ? scheme : MODE_CSDA;
-                        trk.step_X_limit = (cfg.event & EVENT_LIMIT_ENERGY) ?
-                            cel_grammage(
-                                p, tmp_scheme, material, cfg.limit_energy) :
-                            0.;
-                        trk.step_first = 1;
-                        trk.step_invlb1 = 0;
-                }
-
-                ti = state.time;
-                wi = state.weight;
-                Xi = state.grammage;
-                if (cfg.energy_loss >= MODE_CSDA) {
-                        const double ki = state.energy;
-                        Xf = cel_grammage(p, scheme, material, ki);
-                        dei = 1. / cel_energy_loss(p, scheme, material, ki);
-                }
-                transport_limit(
-                    p, cfg, trk, rng, state, material, Xi, Xf, &grammage_max);
-                if (trk.step_event) break;
-        }
-
-        /* Protect the final kinetic energy against rounding errors. */
+/* pumas.c:5492-5513 */
+PB_FN void stepping_finish(const Settings & cfg, State & state)
+{
         if (cfg.direction == MODE_FORWARD) {
                 const double kinetic_min =
                     (cfg.event & EVENT_LIMIT_ENERGY) ? cfg.limit_energy : 0.;
@@ -1157,9 +1050,195 @@ PB_FN int transport_with_stepping(const Physics & p, const Settings & cfg,
                         (double)FLT_EPSILON))
                         state.energy = cfg.limit_energy;
         }
+}
 
-        *medium_ptr = medium;
-        return trk.step_event;
+/* pumas.c:5210-5273. Returns PHASE_STEP, or PHASE_DONE when the track stops
+ * before its first step (then `*final` tells whether the final protections
+ * apply: the reference returns early, skipping them, at :5250-5273). */
+template <class Rng>
+PB_FN int stepping_begin(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+{
+        lp.material = geo.layer[lp.medium].material;
+        const int scheme = cfg.energy_loss;
+        lp.straight = straight_flag(cfg, lp.step_max_locals, lp.locals);
+        lp.first = 1;
+
+        trk.step_event = EVENT_NONE;
+        lp.ti = state.time;
+        lp.wi = state.weight;
+        lp.Xi = state.grammage;
+        if (scheme > MODE_DISABLED) {
+                const double ki = state.energy;
+                lp.Xf = cel_grammage(p, scheme, lp.material, ki);
+                lp.dei = 1. / cel_energy_loss(p, scheme, lp.material, ki);
+        } else {
+                lp.Xf = lp.dei = 0.;
+        }
+        lp.grammage_max = 0.;
+
+        int early = EVENT_NONE;
+        if ((cfg.event & EVENT_LIMIT_DISTANCE) &&
+            (state.distance >= cfg.limit_distance))
+                early = EVENT_LIMIT_DISTANCE;
+        else if ((cfg.event & EVENT_LIMIT_GRAMMAGE) &&
+            (state.grammage >= cfg.limit_grammage))
+                early = EVENT_LIMIT_GRAMMAGE;
+        else if ((cfg.event & EVENT_LIMIT_TIME) &&
+            (state.time >= cfg.limit_time))
+                early = EVENT_LIMIT_TIME;
+        else if (state.weight <= 0.)
+                early = EVENT_WEIGHT;
+        if (early != EVENT_NONE) {
+                trk.step_event = early;
+                return PHASE_DONE;
+        }
+
+        trk.step_event = EVENT_NONE;
+        trk.step_first = 1;
+        trk.step_X_limit = (cfg.event & EVENT_LIMIT_ENERGY) ?
+            cel_grammage(p, (scheme > MODE_DISABLED) ? scheme : MODE_CSDA,
+                lp.material, cfg.limit_energy) :
+            0.;
+        trk.step_invlb1 = 0;
+        transport_limit(p, cfg, trk, rng, state, lp.material, lp.Xi, lp.Xf,
+            &lp.grammage_max);
+        if (trk.step_event) return PHASE_DONE;
+        return PHASE_STEP;
+}
+
+/* pumas.c:5404-5416 and 5476-5488: refresh the locals after a vertex, update
+ * the initial conditions and draw the next limits. */
+template <class Rng>
+PB_FN int stepping_rearm(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp,
+    bool after_vertex)
+{
+        if (after_vertex && (lp.step_max_locals > 0.)) {
+                lp.step_max_locals = set_locals(
+                    p, geo, cfg.accuracy, lp.medium, state, &lp.locals);
+                if (lp.locals.density <= 0.) {
+                        trk.error = RETURN_DENSITY_ERROR;
+                        return PHASE_DONE;
+                }
+        }
+        const int scheme = cfg.energy_loss;
+        lp.ti = state.time;
+        lp.wi = state.weight;
+        lp.Xi = state.grammage;
+        if (cfg.energy_loss >= MODE_CSDA) {
+                const double ki = state.energy;
+                lp.Xf = cel_grammage(p, scheme, lp.material, ki);
+                lp.dei = 1. / cel_energy_loss(p, scheme, lp.material, ki);
+        }
+        transport_limit(p, cfg, trk, rng, state, lp.material, lp.Xi, lp.Xf,
+            &lp.grammage_max);
+        if (trk.step_event) {
+                stepping_finish(cfg, state);
+                return PHASE_DONE;
+        }
+        return PHASE_STEP;
+}
+
+/* One iteration of the stepping loop, pumas.c:5277-5335 and, for a change of
+ * medium, 5417-5467 + re-arm. */
+template <class Rng>
+PB_FN int stepping_step(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+{
+        if (!lp.first) {
+                lp.step_max_type = medium_locate(geo, cfg.direction, state,
+                    false, 0, true, &lp.step_max_medium);
+                if ((lp.step_max_medium > 0.) &&
+                    (lp.step_max_type == STEP_CHECK))
+                        lp.step_max_medium += 0.5 * STEP_MIN;
+        }
+
+        int new_medium = -1;
+        if (!step_transport(p, cfg, geo, trk, rng, state, lp.straight,
+                lp.medium, lp.locals, lp.grammage_max, lp.step_max_medium,
+                lp.step_max_type, &lp.step_max_locals, &new_medium))
+                return PHASE_DONE; /* error: no final protection (:5293) */
+        lp.first = 0;
+
+        if (!trk.step_event) return PHASE_STEP;
+
+        /* Weight update at a boundary or hard loss, pumas.c:5309-5321. */
+        const int scheme = cfg.energy_loss;
+        if ((cfg.direction == MODE_BACKWARD) &&
+            (cfg.energy_loss >= MODE_CSDA)) {
+                const double wt = (cfg.decay == MODE_WEIGHTED) ?
+                    exp(-fabs(state.time - lp.ti) / p.ctau) :
+                    1.;
+                state.weight = lp.wi * wt * lp.dei *
+                    cel_energy_loss(p, scheme, lp.material, state.energy);
+        } else if (cfg.decay == MODE_WEIGHTED) {
+                state.weight = lp.wi * exp(-fabs(state.time - lp.ti) / p.ctau);
+        }
+
+        if (trk.step_event &
+            (EVENT_LIMIT | EVENT_WEIGHT | EVENT_VERTEX_DECAY)) {
+                stepping_finish(cfg, state);
+                return PHASE_DONE;
+        } else if (trk.step_event & EVENT_VERTEX_DEL) {
+                return PHASE_DEL;
+        } else if (trk.step_event & EVENT_VERTEX_COULOMB) {
+                return PHASE_EHS;
+        }
+
+        /* EVENT_MEDIUM */
+        lp.medium = new_medium;
+        if ((lp.medium < 0) || (cfg.event & EVENT_MEDIUM)) {
+                stepping_finish(cfg, state);
+                return PHASE_DONE;
+        }
+        lp.material = geo.layer[lp.medium].material;
+        lp.locals.density = 0.;
+        lp.locals.magnet[0] = lp.locals.magnet[1] = lp.locals.magnet[2] = 0.;
+        lp.locals.magnetized = 0;
+        lp.step_max_locals =
+            set_locals(p, geo, cfg.accuracy, lp.medium, state, &lp.locals);
+        if (lp.locals.density <= 0.) {
+                trk.error = RETURN_DENSITY_ERROR;
+                return PHASE_DONE;
+        }
+        lp.straight = straight_flag(cfg, lp.step_max_locals, lp.locals);
+
+        const int tmp_scheme = scheme > MODE_DISABLED ? scheme : MODE_CSDA;
+        trk.step_X_limit = (cfg.event & EVENT_LIMIT_ENERGY) ?
+            cel_grammage(p, tmp_scheme, lp.material, cfg.limit_energy) :
+            0.;
+        trk.step_first = 1;
+        trk.step_invlb1 = 0;
+        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, false);
+}
+
+/* A hard inelastic event, pumas.c:5340-5392 then re-arm. */
+template <class Rng>
+PB_FN int stepping_del(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+{
+        transport_do_del(p, cfg, trk, rng, state, lp.material);
+        if ((cfg.event & trk.step_event) || trk.step_event == EVENT_WEIGHT) {
+                stepping_finish(cfg, state);
+                return PHASE_DONE;
+        }
+        trk.step_first = 1;
+        trk.step_invlb1 = 0;
+        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, true);
+}
+
+/* A hard elastic event, pumas.c:5393-5402 then re-arm. */
+template <class Rng>
+PB_FN int stepping_ehs(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+{
+        transport_do_ehs(p, cfg, rng, state, lp.material);
+        if (cfg.event & trk.step_event) {
+                stepping_finish(cfg, state);
+                return PHASE_DONE;
+        }
+        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, true);
 }
 
 /* Closed form CSDA in a uniform, field free medium. pumas.c:4777-4949. */
@@ -1327,32 +1406,20 @@ PB_FN int settings_check(const Physics & p, const Settings & cfg)
         return 0;
 }
 
-/* pumas_context_transport for one track, pumas.c:3114-3251. */
+/* Start of pumas_context_transport for one track, pumas.c:3114-3235: checks,
+ * first medium and locals, lifetime draw, then either the closed form CSDA
+ * (the track is then over) or the prologue of the stepping. Returns the phase
+ * of the track; `out` holds rc, the first medium and, when PHASE_DONE is
+ * returned, the end event and last medium. */
 template <class Rng>
-PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Rng & rng, State & state, unsigned int * n_steps)
+PB_FN int track_begin(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Rng & rng, State & state, Track & trk, Loop & lp,
+    Outcome & out)
 {
-        Outcome out;
         out.rc = RETURN_SUCCESS;
         out.event = EVENT_NONE;
         out.medium[0] = out.medium[1] = -1;
-        if (n_steps) *n_steps = 0;
 
-        if (state.decayed) {
-                out.event = EVENT_VERTEX_DECAY;
-                return out;
-        }
-
-        {
-                const double * const u = state.direction;
-                const double norm2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
-                if (fabs(norm2 - 1) > (double)FLT_EPSILON) {
-                        out.rc = 5; /* PUMAS_RETURN_DIRECTION_ERROR */
-                        return out;
-                }
-        }
-
-        Track trk;
         trk.lifetime = 0.;
         trk.step_first = 1;
         trk.step_event = EVENT_NONE;
@@ -1364,6 +1431,20 @@ PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
         trk.error = RETURN_SUCCESS;
         trk.n_steps = 0;
 
+        if (state.decayed) {
+                out.event = EVENT_VERTEX_DECAY;
+                return PHASE_DONE;
+        }
+
+        {
+                const double * const u = state.direction;
+                const double norm2 = u[0] * u[0] + u[1] * u[1] + u[2] * u[2];
+                if (fabs(norm2 - 1) > (double)FLT_EPSILON) {
+                        out.rc = 5; /* PUMAS_RETURN_DIRECTION_ERROR */
+                        return PHASE_DONE;
+                }
+        }
+
         int medium = -1;
         double step_max_medium = 0.;
         const int step_max_type = medium_locate(
@@ -1372,10 +1453,10 @@ PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
         out.medium[1] = -1;
         if (medium < 0) {
                 out.event = EVENT_MEDIUM;
-                return out;
+                return PHASE_DONE;
         } else if ((step_max_medium > 0.) && (step_max_type == STEP_CHECK))
                 step_max_medium += 0.5 * STEP_MIN;
-        Locals locals;
+        Locals & locals = lp.locals;
         locals.density = 0.;
         locals.magnet[0] = locals.magnet[1] = locals.magnet[2] = 0.;
         locals.magnetized = 0;
@@ -1385,7 +1466,7 @@ PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
                 step_max_medium = step_max_locals;
         if (locals.density <= 0.) {
                 out.rc = RETURN_DENSITY_ERROR;
-                return out;
+                return PHASE_DONE;
         }
 
         if (cfg.decay == MODE_RANDOMISED) {
@@ -1399,7 +1480,7 @@ PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
                 if ((cfg.energy_loss == MODE_DISABLED) &&
                     ((cfg.event & EVENT_LIMIT) == 0)) {
                         out.rc = 15; /* PUMAS_RETURN_MISSING_LIMIT */
-                        return out;
+                        return PHASE_DONE;
                 } else if ((cfg.scattering == MODE_DISABLED) &&
                     (cfg.energy_loss == MODE_CSDA) && !locals.magnetized) {
                         /* (magnetised closed form: stepping instead, see the
@@ -1408,17 +1489,58 @@ PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
                 }
         }
 
-        int e;
-        if (do_stepping) {
-                e = transport_with_stepping(p, cfg, geo, trk, rng, state,
-                    &medium, locals, step_max_medium, step_max_type,
-                    step_max_locals);
-        } else {
-                e = transport_with_csda(p, cfg, geo, trk, state, medium, locals);
+        lp.medium = medium;
+        if (!do_stepping) {
+                out.event =
+                    transport_with_csda(p, cfg, geo, trk, state, medium, locals);
+                out.medium[1] = medium;
+                return PHASE_DONE;
         }
-        out.event = e;
-        out.medium[1] = medium;
+
+        lp.step_max_medium = step_max_medium;
+        lp.step_max_type = step_max_type;
+        lp.step_max_locals = step_max_locals;
+        const int phase = stepping_begin(p, cfg, geo, trk, rng, state, lp);
+        if (phase == PHASE_DONE) {
+                out.event = trk.step_event;
+                out.medium[1] = lp.medium;
+                out.rc = trk.error;
+        }
+        return phase;
+}
+
+/* End of a track that went through the stepping, pumas.c:3248-3250. */
+PB_FN void track_end(const Track & trk, const Loop & lp, Outcome & out)
+{
+        out.event = trk.step_event;
+        out.medium[1] = lp.medium;
         out.rc = trk.error;
+}
+
+/* pumas_context_transport for one track run to completion (CPU build and the
+ * reference kernel): the phases chained in sequence. */
+template <class Rng>
+PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
+    const Geometry & geo, Rng & rng, State & state, unsigned int * n_steps)
+{
+        Outcome out;
+        Track trk;
+        Loop lp;
+        int phase = track_begin(p, cfg, geo, rng, state, trk, lp, out);
+        if (phase != PHASE_DONE) {
+                while (phase != PHASE_DONE) {
+                        if (phase == PHASE_STEP)
+                                phase = stepping_step(
+                                    p, cfg, geo, trk, rng, state, lp);
+                        else if (phase == PHASE_EHS)
+                                phase = stepping_ehs(
+                                    p, cfg, geo, trk, rng, state, lp);
+                        else
+                                phase = stepping_del(
+                                    p, cfg, geo, trk, rng, state, lp);
+                }
+                track_end(trk, lp, out);
+        }
         if (n_steps) *n_steps = trk.n_steps;
         return out;
 }
