@@ -376,6 +376,13 @@ PUMAS_API enum pumas_return pumas_b200_context_track_offset_set(
 PUMAS_API enum pumas_return pumas_b200_context_stream_set(
     struct pumas_context * context, void * cuda_stream);
 
+/* New. Select the device kernel: 0 (default) the wavefront kernel, persistent
+ * CTAs that regroup tracks by pending work; 1 the monolithic kernel, one thread
+ * per track for its whole life (kept for A/B parity and profiling). Both give
+ * the same per-track results. */
+PUMAS_API enum pumas_return pumas_b200_context_kernel_set(
+    struct pumas_context * context, int kernel);
+
 /* ------------------------------------------------------------------------
  * Transport
  * ------------------------------------------------------------------------ */

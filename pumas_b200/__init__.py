@@ -192,6 +192,8 @@ def library():
         ctypes.POINTER(ContextStruct), ctypes.c_ulonglong]
     lib.pumas_b200_context_stream_set.argtypes = [
         ctypes.POINTER(ContextStruct), ctypes.c_void_p]
+    lib.pumas_b200_context_kernel_set.argtypes = [
+        ctypes.POINTER(ContextStruct), ctypes.c_int]
     lib.pumas_context_transport_n.argtypes = [
         ctypes.POINTER(ContextStruct), ctypes.c_long, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p]
@@ -323,6 +325,10 @@ class Context:
     def stream(self, cuda_stream):
         _check(library().pumas_b200_context_stream_set(
             self._ptr, ctypes.c_void_p(cuda_stream)))
+
+    def kernel(self, kernel):
+        """0: wavefront kernel (default), 1: monolithic kernel."""
+        _check(library().pumas_b200_context_kernel_set(self._ptr, kernel))
 
     def transport(self, states, events=None, media=None):
         """pumas_context_transport_n on a host numpy array of STATE_DTYPE

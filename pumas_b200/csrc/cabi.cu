@@ -54,6 +54,8 @@ struct ContextImpl {
         unsigned int * d_random;
         unsigned int * d_steps;
         int * d_status;
+        unsigned long long * d_cursor;
+        int kernel;
         long last_n;
         double last_ms;
         int last_launches;
@@ -196,6 +198,10 @@ cudaError_t context_reserve(ContextImpl * c, long n)
                 e = cudaMalloc(&c->d_status, sizeof(int));
                 if (e != cudaSuccess) return e;
         }
+        if (c->d_cursor == nullptr) {
+                e = cudaMalloc(&c->d_cursor, sizeof(unsigned long long));
+                if (e != cudaSuccess) return e;
+        }
         if (!c->events_ready) {
                 e = cudaEventCreate(&c->ev0);
                 if (e == cudaSuccess) e = cudaEventCreate(&c->ev1);
@@ -332,6 +338,7 @@ const char * pumas_error_function(pumas_function_t * caller)
         NAME(pumas_b200_context_geometry_set)
         NAME(pumas_b200_context_track_offset_set)
         NAME(pumas_b200_context_stream_set)
+        NAME(pumas_b200_context_kernel_set)
         NAME(pumas_b200_context_last_counters)
         NAME(pumas_b200_context_last_kernel_time)
         NAME(pumas_error_raise)
@@ -896,6 +903,7 @@ void pumas_context_destroy(struct pumas_context ** context)
         ContextImpl * c = reinterpret_cast<ContextImpl *>(*context);
         context_free_buffers(c);
         if (c->d_status) cudaFree(c->d_status);
+        if (c->d_cursor) cudaFree(c->d_cursor);
         if (c->events_ready) {
                 cudaEventDestroy(c->ev0);
                 cudaEventDestroy(c->ev1);
@@ -1003,6 +1011,21 @@ enum pumas_return pumas_b200_context_track_offset_set(
                 return RAISE(pumas_b200_context_track_offset_set,
                     PUMAS_RETURN_VALUE_ERROR, "no context (null)");
         reinterpret_cast<ContextImpl *>(context)->track_offset = offset;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_b200_context_kernel_set(
+    struct pumas_context * context, int kernel)
+{
+        if (context == nullptr)
+                return RAISE(pumas_b200_context_kernel_set,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        if ((kernel != pb::KERNEL_WAVEFRONT) &&
+            (kernel != pb::KERNEL_MONOLITHIC))
+                return RAISE(pumas_b200_context_kernel_set,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid kernel index [%d]",
+                    kernel);
+        reinterpret_cast<ContextImpl *>(context)->kernel = kernel;
         return PUMAS_RETURN_SUCCESS;
 }
 
@@ -1114,7 +1137,7 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
                 e = pb::launch_transport(physics->d_view, cfg, c->geometry,
                     (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_states,
                     d_events, d_media, c->d_status, c->d_random, c->d_steps,
-                    stream);
+                    c->d_cursor, c->kernel, stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev1, stream);
         int status = 0;
         if ((e == cudaSuccess) && !states_on_device)

@@ -13,13 +13,19 @@ namespace pb {
 
 constexpr int TRANSPORT_BLOCK = 128;
 
-/* Transport n tracks, one thread each. All pointers are device pointers;
- * `status` receives the first non-zero pumas_return raised by a track. Track i
- * draws from the Philox stream (seed, offset + i). */
+enum {
+        KERNEL_WAVEFRONT = 0, /* persistent CTAs regrouping tracks by phase */
+        KERNEL_MONOLITHIC = 1 /* one thread runs one track to completion */
+};
+
+/* Transport n tracks. All pointers are device pointers; `status` receives the
+ * first non-zero pumas_return raised by a track, `cursor` is a scratch work
+ * counter. Track i draws from the Philox stream (seed, offset + i). */
 cudaError_t launch_transport(const Physics & p, const Settings & cfg,
     const Geometry & geo, uint64_t seed, uint64_t offset, long n,
     State * states, int * events, int * media, int * status,
-    unsigned int * n_random, unsigned int * n_steps, cudaStream_t stream);
+    unsigned int * n_random, unsigned int * n_steps,
+    unsigned long long * cursor, int kernel, cudaStream_t stream);
 
 } /* namespace pb */
 
