@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY = os.path.join(HERE, "libpumas_b200.so")
+LIBRARY = os.environ.get(
+    "PUMAS_B200_LIBRARY", os.path.join(HERE, "libpumas_b200.so"))
 
 # ---- enums (include/pumas_b200.h; pumas.h:90-236) ---------------------------
 MODE_DISABLED, MODE_CSDA, MODE_MIXED, MODE_STRAGGLED = -1, 0, 1, 2

@@ -7,7 +7,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-TARGET = os.path.join(HERE, "libpumas_b200.so")
+TARGET = os.environ.get(
+    "PUMAS_B200_TARGET", os.path.join(HERE, "libpumas_b200.so"))
 
 # -fmad=false: no FMA contraction, so that binary64 arithmetic follows the
 # reference's order of operations bit for bit ("Numerics").
@@ -41,7 +42,8 @@ def build(force=False, verbose=False):
     if not force and up_to_date():
         return TARGET
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + [
+    extra = os.environ.get("PUMAS_B200_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + [
         "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-o", TARGET
     ] + sources()
     if verbose:

@@ -54,7 +54,7 @@ struct ContextImpl {
         unsigned int * d_random;
         unsigned int * d_steps;
         int * d_status;
-        unsigned long long * d_cursor;
+        void * d_workspace;
         int kernel;
         long last_n;
         double last_ms;
@@ -198,8 +198,11 @@ cudaError_t context_reserve(ContextImpl * c, long n)
                 e = cudaMalloc(&c->d_status, sizeof(int));
                 if (e != cudaSuccess) return e;
         }
-        if (c->d_cursor == nullptr) {
-                e = cudaMalloc(&c->d_cursor, sizeof(unsigned long long));
+        if (c->d_workspace == nullptr) {
+                size_t bytes = 0;
+                e = pb::transport_workspace_bytes(&bytes);
+                if (e != cudaSuccess) return e;
+                e = cudaMalloc(&c->d_workspace, bytes);
                 if (e != cudaSuccess) return e;
         }
         if (!c->events_ready) {
@@ -903,7 +906,7 @@ void pumas_context_destroy(struct pumas_context ** context)
         ContextImpl * c = reinterpret_cast<ContextImpl *>(*context);
         context_free_buffers(c);
         if (c->d_status) cudaFree(c->d_status);
-        if (c->d_cursor) cudaFree(c->d_cursor);
+        if (c->d_workspace) cudaFree(c->d_workspace);
         if (c->events_ready) {
                 cudaEventDestroy(c->ev0);
                 cudaEventDestroy(c->ev1);
@@ -1137,7 +1140,7 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
                 e = pb::launch_transport(physics->d_view, cfg, c->geometry,
                     (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_states,
                     d_events, d_media, c->d_status, c->d_random, c->d_steps,
-                    c->d_cursor, c->kernel, stream);
+                    c->d_workspace, c->kernel, stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev1, stream);
         int status = 0;
         if ((e == cudaSuccess) && !states_on_device)

@@ -18,14 +18,19 @@ enum {
         KERNEL_MONOLITHIC = 1 /* one thread runs one track to completion */
 };
 
+/* Size of the device scratch buffer launch_transport needs (work cursor and
+ * the parked tracks of the wavefront kernel). */
+cudaError_t transport_workspace_bytes(size_t * bytes);
+
 /* Transport n tracks. All pointers are device pointers; `status` receives the
- * first non-zero pumas_return raised by a track, `cursor` is a scratch work
- * counter. Track i draws from the Philox stream (seed, offset + i). */
+ * first non-zero pumas_return raised by a track, `workspace` is a scratch
+ * buffer of transport_workspace_bytes(). Track i draws from the Philox stream
+ * (seed, offset + i). */
 cudaError_t launch_transport(const Physics & p, const Settings & cfg,
     const Geometry & geo, uint64_t seed, uint64_t offset, long n,
     State * states, int * events, int * media, int * status,
-    unsigned int * n_random, unsigned int * n_steps,
-    unsigned long long * cursor, int kernel, cudaStream_t stream);
+    unsigned int * n_random, unsigned int * n_steps, void * workspace,
+    int kernel, cudaStream_t stream);
 
 } /* namespace pb */
 

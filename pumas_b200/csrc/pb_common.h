@@ -26,6 +26,25 @@
 
 namespace pb {
 
+/* Out-of-line libm calls. Inlined, each CUDA log / exp / sincos / pow is 60 to
+ * 300 instructions; the transport code calls them at ~150 sites, which alone
+ * made the kernel several times larger than the instruction cache and
+ * `no_instruction` its first stall reason (profiles/r1_v1). One shared copy
+ * each keeps the stepping loop cache resident; results are unchanged. */
+#if defined(__CUDACC__)
+#define PB_MATH inline __host__ __device__ __noinline__
+#else
+#define PB_MATH inline
+#endif
+PB_MATH double xlog(double x) { return log(x); }
+PB_MATH double xexp(double x) { return exp(x); }
+PB_MATH double xsin(double x) { return sin(x); }
+PB_MATH double xcos(double x) { return cos(x); }
+PB_MATH double xatan(double x) { return atan(x); }
+PB_MATH double xacos(double x) { return acos(x); }
+PB_MATH double xlog10(double x) { return log10(x); }
+PB_MATH double xpow(double x, double y) { return pow(x, y); }
+
 /* pumas.c:60-125 */
 constexpr int N_SCHEMES = 2;
 constexpr int N_LARMOR_ORDERS = 8;

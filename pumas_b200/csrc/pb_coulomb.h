@@ -78,13 +78,13 @@ PB_FN void coulomb_screening_parameters(const Element & el, double mass,
                 f *= zeta2;
         } else {
                 const double r2i = 1. / (1. + zeta2);
-                const double phi = -atan(sqrt(zeta2));
-                f = -0.5 * log(r2i) + 0.5 * (1. - r2i) +
-                    1. / 12. * (1. - cos(2 * phi) * r2i) -
-                    1. / 120. * (1. - cos(4 * phi) * r2i * r2i) +
-                    1. / 252. * (1. - cos(6 * phi) * r2i * r2i * r2i);
+                const double phi = -xatan(sqrt(zeta2));
+                f = -0.5 * xlog(r2i) + 0.5 * (1. - r2i) +
+                    1. / 12. * (1. - xcos(2 * phi) * r2i) -
+                    1. / 120. * (1. - xcos(4 * phi) * r2i * r2i) +
+                    1. / 252. * (1. - xcos(6 * phi) * r2i * r2i * r2i);
         }
-        const double ktv = exp(2 * f);
+        const double ktv = xexp(2 * f);
 
         const double p02 = kinetic0 * (kinetic0 + 2. * mass);
         const double d = 0.25 * HBAR_C * HBAR_C / p02 * ktv;
@@ -115,7 +115,7 @@ PB_FN double coulomb_nuclear_form_factor(double mu, double N)
                 d = 1. / (1. + 0.1 * x2);
         } else {
                 const double x = sqrt(x2);
-                d = 3 * (sin(x) - x * cos(x)) / (x2 * x);
+                d = 3 * (xsin(x) - x * xcos(x)) / (x2 * x);
         }
         return d * d;
 }
@@ -143,7 +143,7 @@ PB_FN void coulomb_data_set(
 }
 
 /* Logarithm in the working precision R. */
-PB_FN double real_log(double x) { return log(x); }
+PB_FN double real_log(double x) { return xlog(x); }
 PB_FN dd real_log(const dd & x) { return dd_log(x); }
 #if !defined(__CUDA_ARCH__)
 inline long double real_log(long double x) { return logl(x); }

@@ -8,7 +8,7 @@
  *   - the ionisation DCS and its sampler (pumas.c:11082-11226)      [a17]
  *   - the exact models (pumas.c:13915, 14394-14604, 14626-15083),
  *     the dilogarithm (pumas.c:12609) and the kinematic ranges      [a18]
- * Element constants that the reference recomputes with pow() on every call
+ * Element constants that the reference recomputes with xpow() on every call
  * (Z^(1/3), A^0.27 ...) are taken from `Element`, where the host evaluated the
  * same expressions with the same libm at load time.
  */
@@ -338,24 +338,24 @@ PB_NOINLINE double dcs_bremsstrahlung_SSR(
         const double mu_qc = m / (MMU * p.c_exp_1 / Dn);
         const double rho = sqrt(1. + 4. * mu_qc * mu_qc);
 
-        const double log_rho = log((rho + 1.) / (rho - 1.));
-        const double delta1 = log(mu_qc) + 0.5 * rho * log_rho;
-        const double delta2 = log(mu_qc) +
+        const double log_rho = xlog((rho + 1.) / (rho - 1.));
+        const double delta1 = xlog(mu_qc) + 0.5 * rho * log_rho;
+        const double delta2 = xlog(mu_qc) +
             0.25 * (3. * rho - rho * rho * rho) * log_rho + 2. * mu_qc * mu_qc;
 
         const double delta = m * m * v / (2. * energy * (1. - v));
 
-        double phi1 = log(rad_log * Z13 * (m / ME) /
+        double phi1 = xlog(rad_log * Z13 * (m / ME) /
             (1. + rad_log * Z13 * p.c_exp_1_2 * delta / ME));
-        double phi2 = log(rad_log * Z13 * p.c_exp_m1_6 * (m / ME) /
+        double phi2 = xlog(rad_log * Z13 * p.c_exp_m1_6 * (m / ME) /
             (1. + rad_log * Z13 * p.c_exp_1_3 * delta / ME));
         phi1 -= delta1 * (1. - 1. / Z);
         phi2 -= delta2 * (1. - 1. / Z);
 
         const double s_atomic_1 =
-            log(m / delta / (m * delta / (ME * ME) + SQRTE));
+            xlog(m / delta / (m * delta / (ME * ME) + SQRTE));
         const double s_atomic_2 =
-            log(1. + ME / (delta * rad_log_inel * Z13 * Z13 * SQRTE));
+            xlog(1. + ME / (delta * rad_log_inel * Z13 * Z13 * SQRTE));
         const double s_atomic =
             (4. / 3. * (1. - v) + v * v) * (s_atomic_1 - s_atomic_2);
 
@@ -369,13 +369,13 @@ PB_NOINLINE double dcs_bremsstrahlung_SSR(
                     1407.77 * v * v * v;
         } else if (v >= 0.01 && v < 0.9) {
                 s_rad = -2.8922 + -19.0156 * v + 57.698 * v * v;
-                const double tmp = log(1. - v);
-                s_rad += -63.418 * v * log(v) + 14.1166 * tmp +
+                const double tmp = xlog(1. - v);
+                s_rad += -63.418 * v * xlog(v) + 14.1166 * tmp +
                     1.84206 * tmp * tmp;
         } else {
                 s_rad = 2134.19 + 581.823 * v + -2708.85 * v * v;
-                const double tmp = log(1. - v);
-                s_rad += 4767.05 * v * log(v) + 1.52918 * tmp +
+                const double tmp = xlog(1. - v);
+                s_rad += 4767.05 * v * xlog(v) + 1.52918 * tmp +
                     0.361933 * tmp * tmp;
         }
 
@@ -415,22 +415,22 @@ PB_NOINLINE double math_dilog(double x)
         if (T <= -2) {
                 Y = -1. / (1. + T);
                 S = 1.;
-                const double l0 = log(-T), l1 = log(1. + 1. / T);
+                const double l0 = xlog(-T), l1 = xlog(1. + 1. / T);
                 A = -PI3 + 0.5 * (l0 * l0 - l1 * l1);
         } else if (T < -1.) {
                 Y = -1. - T;
                 S = -1.;
-                A = log(-T);
-                A = -PI6 + A * (A + log(1. + 1. / T));
+                A = xlog(-T);
+                A = -PI6 + A * (A + xlog(1. + 1. / T));
         } else if (T <= -0.5) {
                 Y = -(1. + T) / T;
                 S = 1.;
-                A = log(-T);
-                A = -PI6 + A * (-0.5 * A + log(1. + T));
+                A = xlog(-T);
+                A = -PI6 + A * (-0.5 * A + xlog(1. + T));
         } else if (T < 0.) {
                 Y = -T / (1. + T);
                 S = -1.;
-                const double l = log(1 + T);
+                const double l = xlog(1 + T);
                 A = 0.5 * (l * l);
         } else if (T <= 1.) {
                 Y = T;
@@ -439,7 +439,7 @@ PB_NOINLINE double math_dilog(double x)
         } else {
                 Y = 1. / T;
                 S = -1.;
-                const double l = log(T);
+                const double l = xlog(T);
                 A = PI6 + 0.5 * (l * l);
         }
 
@@ -490,11 +490,11 @@ PB_NOINLINE double dcs_pair_production_d2_SSR(const Physics & p,
                 g2 = 5.3E-05;
         }
 
-        const double zeta1 = (0.073 * log(energy / m /
+        const double zeta1 = (0.073 * xlog(energy / m /
                                       (1. + g1 * el.z23 * energy / m)) -
             0.26);
         const double zeta2 =
-            (0.058 * log(energy / m / (1 + g2 / Z13 * energy / m)) - 0.14);
+            (0.058 * xlog(energy / m / (1 + g2 / Z13 * energy / m)) - 0.14);
         double zeta;
         if ((zeta1 > 0.) && (zeta2 > 0.)) {
                 zeta = zeta1 / zeta2;
@@ -508,15 +508,15 @@ PB_NOINLINE double dcs_pair_production_d2_SSR(const Physics & p,
 
         /* Diagram e */
         const double Be = ((2. + rho2) * (1. + beta) + xi * (3. + rho2)) *
-                log(1. + 1. / xi) +
+                xlog(1. + 1. / xi) +
             (1. - rho2 - beta) / (1. + xi) - (3. + rho2);
         const double Ce2 = ((1. - rho2) * (1. + beta) + xi * (3. - rho2)) *
-                log(1. + 1. / xi) +
+                xlog(1. + 1. / xi) +
             2. * (1. - beta - rho2) / (1. + xi) - (3. - rho2);
         const double Ce1 = Be - Ce2;
         const double De = ((2. + rho2) * (1. + beta) + xi * (3. + rho2)) *
                 math_dilog(1. / (1. + xi)) -
-            (2. + rho2) * xi * log(1. + 1. / xi) -
+            (2. + rho2) * xi * xlog(1. + 1. / xi) -
             (xi + rho2 + beta) / (1. + xi);
 
         const double med = ME / m * d_n;
@@ -524,27 +524,27 @@ PB_NOINLINE double dcs_pair_production_d2_SSR(const Physics & p,
         double Le1, Le2;
         if (De / Be > 0.) {
                 const double tmp = De / Be;
-                const double Xe = (tmp < 100) ? exp(-tmp) : 0.;
-                Le1 = log(rad_log * Z13 * sqrt(1. + xi) /
+                const double Xe = (tmp < 100) ? xexp(-tmp) : 0.;
+                Le1 = xlog(rad_log * Z13 * sqrt(1. + xi) /
                           (Xe + 2. * ME * p.c_exp_1_2 * rad_log * Z13 *
                                   (1. + xi) / (energy * v * (1. - rho2)))) -
-                    tmp - 0.5 * log(Xe + med2 * (1. + xi));
-                Le2 = log(rad_log * Z13 * p.c_exp_m1_6 * sqrt(1 + xi) /
+                    tmp - 0.5 * xlog(Xe + med2 * (1. + xi));
+                Le2 = xlog(rad_log * Z13 * p.c_exp_m1_6 * sqrt(1 + xi) /
                           (Xe + 2. * ME * p.c_exp_1_3 * rad_log * Z13 *
                                   (1. + xi) / (energy * v * (1. - rho2)))) -
-                    tmp - 0.5 * log(Xe + med2 * p.c_exp_m1_3 * (1. + xi));
+                    tmp - 0.5 * xlog(Xe + med2 * p.c_exp_m1_3 * (1. + xi));
         } else {
                 const double tmp = De / Be;
-                const double Xe_inv = (tmp > -100) ? exp(De / Be) : 0;
-                Le1 = log(rad_log * Z13 * sqrt(1. + xi) /
+                const double Xe_inv = (tmp > -100) ? xexp(De / Be) : 0;
+                Le1 = xlog(rad_log * Z13 * sqrt(1. + xi) /
                           (1. + Xe_inv * 2. * ME * p.c_exp_1_2 * rad_log * Z13 *
                                   (1. + xi) / (energy * v * (1. - rho2)))) -
-                    0.5 * De / Be - 0.5 * log(1. + Xe_inv * med2 * (1. + xi));
-                Le2 = log(rad_log * Z13 * p.c_exp_m1_6 * sqrt(1 + xi) /
+                    0.5 * De / Be - 0.5 * xlog(1. + Xe_inv * med2 * (1. + xi));
+                Le2 = xlog(rad_log * Z13 * p.c_exp_m1_6 * sqrt(1 + xi) /
                           (1. + Xe_inv * 2. * ME * p.c_exp_1_3 * rad_log * Z13 *
                                   (1. + xi) / (energy * v * (1. - rho2)))) -
                     0.5 * De / Be -
-                    0.5 * log(1. + Xe_inv * med2 * p.c_exp_m1_3 * (1. + xi));
+                    0.5 * xlog(1. + Xe_inv * med2 * p.c_exp_m1_3 * (1. + xi));
         }
 
         double diagram_e = const_prefactor * (Z + zeta) * (1. - v) / v *
@@ -554,17 +554,17 @@ PB_NOINLINE double dcs_pair_production_d2_SSR(const Physics & p,
         /* Diagram mu */
         const double Bm = ((1. + rho2) * (1. + (3. * beta) / 2) -
                               1. / xi * (1. + 2. * beta) * (1. - rho2)) *
-                log(1. + xi) +
+                xlog(1. + xi) +
             xi * (1. - rho2 - beta) / (1. + xi) + (1. + 2. * beta) * (1. - rho2);
         const double Cm2 = ((1. - beta) * (1. - rho2) - xi * (1. + rho2)) *
-                log(1. + xi) / xi -
+                xlog(1. + xi) / xi -
             2. * (1. - beta - rho2) / (1. + xi) + 1. - beta -
             (1. + beta) * rho2;
         const double Cm1 = Bm - Cm2;
         const double Dm = ((1. + rho2) * (1. + (3. * beta) / 2.) -
                               1. / xi * (1. + 2. * beta) * (1. - rho2)) *
                 math_dilog(xi / (1. + xi)) +
-            (1. + (3. * beta) / 2.) * (1. - rho2) / xi * log(1. + xi) +
+            (1. + (3. * beta) / 2.) * (1. - rho2) / xi * xlog(1. + xi) +
             (1. - rho2 - beta / 2. * (1. + rho2) +
                 (1. - rho2) / (2. * xi) * beta) *
                 xi / (1. + xi);
@@ -572,22 +572,22 @@ PB_NOINLINE double dcs_pair_production_d2_SSR(const Physics & p,
         double Lm1, Lm2;
         if (Dm / Bm > 0.) {
                 const double tmp = Dm / Bm;
-                const double Xm = (tmp < 100) ? exp(-tmp) : 0.;
-                Lm1 = log(m / ME * rad_log * Z13 / d_n /
+                const double Xm = (tmp < 100) ? xexp(-tmp) : 0.;
+                Lm1 = xlog(m / ME * rad_log * Z13 / d_n /
                           (Xm + 2. * ME * p.c_exp_1_2 * rad_log * Z13 *
                                   (1. + xi) / (energy * v * (1. - rho2)))) -
                     tmp;
-                Lm2 = log(m / ME * rad_log * Z13 / d_n /
+                Lm2 = xlog(m / ME * rad_log * Z13 / d_n /
                           (Xm + 2. * ME * p.c_exp_1_3 * rad_log * Z13 *
                                   (1. + xi) / (energy * v * (1. - rho2)))) -
                     tmp;
         } else {
                 const double tmp = Dm / Bm;
-                const double Xmv = (tmp > -100) ? exp(tmp) : 0.;
-                Lm1 = log(m / ME * rad_log * Z13 / d_n /
+                const double Xmv = (tmp > -100) ? xexp(tmp) : 0.;
+                Lm1 = xlog(m / ME * rad_log * Z13 / d_n /
                     (1. + 2. * ME * p.c_exp_1_2 * rad_log * Z13 * (1. + xi) /
                             (energy * v * (1. - rho2)) * Xmv));
-                Lm2 = log(m / ME * rad_log * Z13 / d_n /
+                Lm2 = xlog(m / ME * rad_log * Z13 / d_n /
                     (1. + 2. * ME * p.c_exp_1_3 * rad_log * Z13 * (1. + xi) /
                             (energy * v * (1. - rho2)) * Xmv));
         }
@@ -623,13 +623,13 @@ PB_NOINLINE double dcs_pair_production_SSR(
         }
         const double ri = 1. - rmax;
         if ((ri <= 0.) || (ri >= 1.)) return 0.;
-        const double tmin = log(ri);
+        const double tmin = xlog(ri);
 
         const double xGQ[12] = PB_GQ12_X;
         const double wGQ[12] = PB_GQ12_W;
         double I = 0.;
         for (int i = 0; i < 12; i++) {
-                const double rho = exp(xGQ[i] * tmin);
+                const double rho = xexp(xGQ[i] * tmin);
                 I -= dcs_pair_production_d2_SSR(p, el, mass, K, q, rho) * rho *
                     wGQ[i] * tmin;
         }
@@ -656,18 +656,18 @@ PB_NOINLINE double dcs_photonuclear_f2p_ALLM97(double x, double Q2)
         const double M = 0.5 * (PROTON_MASS + NEUTRON_MASS);
         const double M2 = M * M;
         const double W2 = M2 + Q2 * (1.0 / x - 1.0);
-        const double t = log(log((Q2 + Q02) / Lambda2) / log(Q02 / Lambda2));
+        const double t = xlog(xlog((Q2 + Q02) / Lambda2) / xlog(Q02 / Lambda2));
         const double xP = (Q2 + mP2) / (Q2 + mP2 + W2 - M2);
         const double xR = (Q2 + mR2) / (Q2 + mR2 + W2 - M2);
-        const double cP = cP1 + (cP1 - cP2) * (1.0 / (1.0 + pow(t, cP3)) - 1.0);
-        const double aP = aP1 + (aP1 - aP2) * (1.0 / (1.0 + pow(t, aP3)) - 1.0);
-        const double bP = bP1 + bP2 * pow(t, bP3);
-        const double cR = cR1 + cR2 * pow(t, cR3);
-        const double aR = aR1 + aR2 * pow(t, aR3);
-        const double bR = bR1 + bR2 * pow(t, bR3);
+        const double cP = cP1 + (cP1 - cP2) * (1.0 / (1.0 + xpow(t, cP3)) - 1.0);
+        const double aP = aP1 + (aP1 - aP2) * (1.0 / (1.0 + xpow(t, aP3)) - 1.0);
+        const double bP = bP1 + bP2 * xpow(t, bP3);
+        const double cR = cR1 + cR2 * xpow(t, cR3);
+        const double aR = aR1 + aR2 * xpow(t, aR3);
+        const double bR = bR1 + bR2 * xpow(t, bR3);
 
-        const double F2P = cP * exp(aP * log(xP) + bP * log(1 - x));
-        const double F2R = cR * exp(aR * log(xR) + bR * log(1 - x));
+        const double F2P = cP * xexp(aP * xlog(xP) + bP * xlog(1 - x));
+        const double F2R = cR * xexp(aR * xlog(xR) + bR * xlog(1 - x));
         return Q2 / (Q2 + m02) * (F2P + F2R);
 }
 
@@ -676,9 +676,9 @@ PB_FN double dcs_photonuclear_shadowing_DRSS(const Element & el, double x)
 {
         if (el.Z == 1.) return 1.;
         if (x < 0.0014)
-                return exp(-0.1 * el.lnA);
+                return xexp(-0.1 * el.lnA);
         else if (x < 0.04)
-                return exp((0.069 * log10(x) + 0.097) * el.lnA);
+                return xexp((0.069 * xlog10(x) + 0.097) * el.lnA);
         else
                 return 1.;
 }
@@ -728,12 +728,12 @@ PB_NOINLINE double dcs_photonuclear_DRSS(
 
         const double x9[9] = PB_GQ9_X;
         const double w9[9] = PB_GQ9_W;
-        const double xmin = log(Q2min);
-        const double xmax = log(Q2max);
+        const double xmin = xlog(Q2min);
+        const double xmax = xlog(Q2max);
         const double dx = xmax - xmin;
         double ds = 0.;
         for (int i = 0; i < 9; i++) {
-                const double Q2 = exp(xmin + dx * x9[i]);
+                const double Q2 = xexp(xmin + dx * x9[i]);
                 const double w = w9[i] * (dx * Q2);
                 const double tmp = dcs_photonuclear_d2_DRSS(el, ml, K, q, Q2);
                 if (tmp <= 0.) continue;

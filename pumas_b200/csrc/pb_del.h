@@ -28,9 +28,9 @@ struct DelInfo {
 PB_FN double envelope_norm(double a, double xmin, double xmax)
 {
         if (a == 1) {
-                return log(xmax / xmin);
+                return xlog(xmax / xmin);
         } else {
-                return (pow(xmin, 1. - a) - pow(xmax, 1. - a)) / (a - 1.);
+                return (xpow(xmin, 1. - a) - xpow(xmax, 1. - a)) / (a - 1.);
         }
 }
 
@@ -213,15 +213,15 @@ PB_FN bool del_randomise_forward(const Physics & p, const Settings & cfg,
                         u = (u - p0) / (1. - p0);
                 }
                 if (a == 1) {
-                        x = xmin * exp(u * log(xmax / xmin));
+                        x = xmin * xexp(u * xlog(xmax / xmin));
                 } else {
                         const double am = a - 1.;
-                        const double pmin = pow(xmin, -am);
-                        const double pmax = pow(xmax, -am);
-                        x = pow(pmin - u * (pmin - pmax), -1. / am);
+                        const double pmin = xpow(xmin, -am);
+                        const double pmax = xpow(xmax, -am);
+                        x = xpow(pmin - u * (pmin - pmax), -1. / am);
                 }
 
-                const double penv = b0 * pow(x, -a0) + b1 * pow(x, -a1);
+                const double penv = b0 * xpow(x, -a0) + b1 * xpow(x, -a1);
                 const double d = dcs_evaluate(p, info.process, info.element,
                     state.energy, state.energy * x);
                 if (rng.uniform() * penv <= d) break;
@@ -242,22 +242,22 @@ PB_FN void del_randomise_power_law(Rng & rng, double alpha, double xmin,
 {
         double r = 0., w_bias;
         if (alpha == 1.) {
-                const double lnq = log(xmax / xmin);
+                const double lnq = xlog(xmax / xmin);
                 for (;;) {
                         const double z = rng.uniform();
-                        r = xmin * exp(z * lnq);
+                        r = xmin * xexp(z * lnq);
                         if ((r < xmin) || (r >= xmax)) continue;
                         w_bias = lnq * r;
                         break;
                 }
         } else {
                 const double a1 = 1. - alpha;
-                const double x0 = pow(xmin, a1);
-                const double x1 = pow(xmax, a1);
+                const double x0 = xpow(xmin, a1);
+                const double x1 = xpow(xmax, a1);
                 for (;;) {
                         const double z = rng.uniform();
                         const double tmp = x0 + z * (x1 - x0);
-                        r = pow(tmp, 1. / a1);
+                        r = xpow(tmp, 1. / a1);
                         if ((r < xmin) || (r >= xmax)) continue;
                         w_bias = (x1 - x0) * r / (a1 * tmp);
                         break;
@@ -272,11 +272,11 @@ template <class Rng>
 PB_FN bool del_randomise_reverse(const Physics & p, const Settings & cfg,
     Rng & rng, State & state, int material, int * process, int * element)
 {
-        const double lnq0 = -log(p.cutoff);
+        const double lnq0 = -xlog(p.cutoff);
         const double kt = p.Kt[material];
         const double kf = state.energy;
         const double pCEL =
-            (kf >= kt) ? 0. : lnq0 / (lnq0 + log(kt / (kt - kf)));
+            (kf >= kt) ? 0. : lnq0 / (lnq0 + xlog(kt / (kt - kf)));
         if (pCEL && (rng.uniform() < pCEL)) {
                 state.weight /= pCEL;
                 return false;

@@ -79,7 +79,7 @@ PB_FN double set_locals(const Physics & p, const Geometry & g, double accuracy,
         locals->magnet[1] = l.magnet[1];
         locals->magnet[2] = l.magnet[2];
         if (l.density_model == PUMAS_B200_DENSITY_EXPONENTIAL) {
-                locals->density = l.density * exp(-state.position[2] / l.scale);
+                locals->density = l.density * xexp(-state.position[2] / l.scale);
                 const double uz = fabs(state.direction[2]);
                 step_max = l.scale / ((uz <= l.eps) ? l.eps : uz);
         } else {

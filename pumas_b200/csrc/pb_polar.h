@@ -39,7 +39,7 @@ PB_NOINLINE double polar_bremsstrahlung(
                 const double q = muni;
                 const double r = mu0;
                 const double qr = q * r;
-                x0 = (1. + 2 * qr) * log((1. + qr) / (r + qr)) -
+                x0 = (1. + 2 * qr) * xlog((1. + qr) / (r + qr)) -
                     (1. - r) * (1 + 2 * q) / (1 + q);
         }
 
@@ -64,7 +64,7 @@ PB_NOINLINE double polar_bremsstrahlung(
                 const double qr = q * r;
                 if (qr > 1E+05) continue;
 
-                const double x = (1. + 2 * qr) * log((1. + qr) / (r + qr)) -
+                const double x = (1. + 2 * qr) * xlog((1. + qr) / (r + qr)) -
                     (1. - r) * (1 + 2 * q) / (1 + q);
 
                 pdf *= x / x0;
@@ -79,7 +79,7 @@ struct PhotonuclearObjective {
         double ml, K, q;
         PB_FN double operator()(double lnQ2) const
         {
-                const double Q2 = exp(lnQ2);
+                const double Q2 = xexp(lnQ2);
                 return -dcs_photonuclear_d2_DRSS(*el, ml, K, q, Q2) * Q2;
         }
 };
@@ -236,14 +236,14 @@ PB_NOINLINE double polar_photonuclear(
         objective.q = q;
 
         double fopt = 0., xopt = 0.;
-        const double lnQ2min = log(Q2min);
-        const double lnQ2max = log(Q2max);
+        const double lnQ2min = xlog(Q2min);
+        const double lnQ2max = xlog(Q2max);
         const int status = math_find_minimum(
             objective, lnQ2min, lnQ2max, 1E-06, 100, &xopt, &fopt);
         fopt = -fopt;
         if (status == -2) return 0.;
 
-        const double x = exp(xopt) / (2 * q * M);
+        const double x = xexp(xopt) / (2 * q * M);
         const double lne = 0.1;
         if ((x <= 0.04) && (xopt + lne < lnQ2max)) {
                 double f2 = 0., x2 = 0.;
@@ -263,7 +263,7 @@ PB_NOINLINE double polar_photonuclear(
         int i;
         for (i = 0; i < 100; i++) {
                 const double u = rng.uniform();
-                Q2 = Q2min * exp(rQ2 * u);
+                Q2 = Q2min * xexp(rQ2 * u);
                 const double r =
                     dcs_photonuclear_d2_DRSS(el, ml, ki, q, Q2) * Q2;
                 if (rng.uniform() * fopt <= r) break;

@@ -48,6 +48,7 @@ struct Track {
         double step_invlb1;
         int randn_done;
         double randn_next;
+        int iK;              /* grid cell of the last located kinetic energy */
         int error;           /* enum pumas_return raised inside the stepping */
         unsigned int n_steps; /* diagnostics: calls of step_transport */
 };
@@ -58,10 +59,10 @@ template <class Rng> PB_FN double step_randn(Track & trk, Rng & rng)
         trk.randn_done = !trk.randn_done;
         if (!trk.randn_done) return trk.randn_next;
 
-        const double r = sqrt(-2. * log(rng.uniform()));
+        const double r = sqrt(-2. * xlog(rng.uniform()));
         const double phi = 2. * PI * rng.uniform();
-        const double c = cos(phi);
-        const double s = sin(phi);
+        const double c = xcos(phi);
+        const double s = xsin(phi);
         trk.randn_next = r * c;
         return r * s;
 }
@@ -111,34 +112,41 @@ PB_FN void step_rotate_direction(Rng & rng, State & state, double mu)
         const double u1z = u0x * direction[1] - u0y * direction[0];
 
         const double phi = PI * (1. - 2. * rng.uniform());
-        const double cp = cos(phi);
-        const double sp = sin(phi);
+        const double cp = xcos(phi);
+        const double sp = xsin(phi);
         direction[0] = cos_theta * direction[0] + st * (cp * u0x + sp * u1x);
         direction[1] = cos_theta * direction[1] + st * (cp * u0y + sp * u1y);
         direction[2] = cos_theta * direction[2] + st * (cp * u0z + sp * u1z);
 }
 
-/* PENELOPE style straggling of the continuous loss. pumas.c:6943-7005. */
+/* PENELOPE style straggling of the continuous loss. pumas.c:6943-7005.
+ * `l0` is the located start energy; the end energy of the continuous loss is
+ * located through `kl`. */
 template <class Rng>
 PB_FN void step_fluctuate(const Physics & p, const Settings & cfg, Track & trk,
-    Rng & rng, const State & state, int material, double Xtot, double dX,
-    double * kf, double * ratio)
+    Rng & rng, const State & state, int material, KLocator & kl, const Loc & l0,
+    double Xtot, double dX, double * kf, double * ratio)
 {
         const int scheme = cfg.energy_loss;
         const double sgn = (cfg.direction == MODE_FORWARD) ? 1. : -1.;
         double k1, r = 0.;
-        k1 = cel_kinetic_energy(p, scheme, material, Xtot - sgn * dX);
+        {
+                const Loc lx = locate_near(p,
+                    col_sm(p, p.X, scheme, material), Xtot - sgn * dX, l0.i);
+                k1 = cel_kinetic_energy_at(p, scheme, material, lx);
+        }
         const double dk0 = fabs(state.energy - k1);
         if ((k1 > 0.) && (dk0 > 0.)) {
-                const double Omega0 = cel_straggling(p, material, state.energy);
-                const double Omega1 = cel_straggling(p, material, k1);
+                const Loc l1 = klocate(p, kl, k1);
+                const double Omega0 = cel_straggling_at(p, material, l0);
+                const double Omega1 = cel_straggling_at(p, material, l1);
                 double dk12 = 0.5 * dX * (Omega0 + Omega1);
                 const double tmp = dX / Xtot;
                 if (tmp > 5E-02) {
                         const double de1 =
-                            cel_energy_loss(p, scheme, material, k1);
+                            cel_energy_loss_at(p, scheme, material, l1);
                         const double de0 =
-                            cel_energy_loss(p, scheme, material, state.energy);
+                            cel_energy_loss_at(p, scheme, material, l0);
                         dk12 *= 1. + sgn * dX / dk0 * (de1 - de0);
                 }
                 const double dk1 = sqrt(dk12);
@@ -211,7 +219,7 @@ PB_FN void transport_limit(const Physics & p, const Settings & cfg, Track & trk,
                 if (cfg.scattering == MODE_MIXED) {
                         const double X = Xi -
                             coulomb_ehs_length(p, material, state.energy) *
-                                log(rng.uniform());
+                                xlog(rng.uniform());
                         if ((*grammage_max == 0.) || (X < *grammage_max)) {
                                 *grammage_max = X;
                                 trk.step_foreseen = EVENT_VERTEX_COULOMB;
@@ -231,7 +239,7 @@ PB_FN void transport_limit(const Physics & p, const Settings & cfg, Track & trk,
 
                         const double nI =
                             del_interaction_length(p, material, state.energy) +
-                            sgn * log(zeta);
+                            sgn * xlog(zeta);
                         if (nI <= 0.) break;
 
                         const double k = del_kinetic_from_interaction_length(
@@ -255,7 +263,7 @@ PB_FN void transport_limit(const Physics & p, const Settings & cfg, Track & trk,
         if ((scheme < MODE_STRAGGLED) && (cfg.scattering == MODE_MIXED)) {
                 const double nI =
                     ehs_interaction_length(p, scheme, material, state.energy) +
-                    sgn * log(rng.uniform());
+                    sgn * xlog(rng.uniform());
                 if (nI > 0.) {
                         const double k = ehs_kinetic_from_interaction_length(
                             p, scheme, material, nI);
@@ -349,12 +357,13 @@ PB_NOINLINE double coulomb_cs_hard(const Physics & p, int component,
 /* pumas.c:5768-5885 */
 template <class Rng>
 PB_FN void transport_do_ehs(const Physics & p, const Settings & cfg, Rng & rng,
-    State & state, int material)
+    State & state, int material, int hint)
 {
         const double kinetic = state.energy;
 
         double mu0 = 0., invlb1 = 0.;
-        table_get_msc(p, cfg.energy_loss, material, kinetic, &mu0, &invlb1);
+        table_get_msc_at(p, cfg.energy_loss, material,
+            locate_near(p, p.K, kinetic, hint), &mu0, &invlb1);
 
         /* Randomise the hard scatterer element. For a single element material
          * the outcome is forced, whatever the cross-section; the variate is
@@ -450,8 +459,15 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
         const double density_i = 1. / density;
         const double momentum = sqrt(state.energy * (state.energy + 2. * p.mass));
 
+        /* The energies of this step are each located once in the grid. */
+        KLocator kl;
+        klocator_init(kl, trk.iK);
+        const Loc l0 = klocate(p, kl, state.energy);
+        const double * const Xcol = col_sm(p, p.X,
+            (scheme == MODE_DISABLED) ? MODE_CSDA : scheme, material);
+
         const int tmp_scheme = (scheme == MODE_DISABLED) ? MODE_CSDA : scheme;
-        const double Xtot = cel_grammage(p, tmp_scheme, material, state.energy);
+        const double Xtot = cel_grammage_at(p, tmp_scheme, material, l0);
 
         /* Local step length. */
         double step_loc, rLarmor0 = 0., uT0[3] = { 0., 0., 0. };
@@ -469,8 +485,8 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                 if (cfg.scattering == MODE_MIXED) {
                         if (trk.step_first != 0) {
                                 double mu0;
-                                table_get_msc(p, cfg.energy_loss, material,
-                                    state.energy, &mu0, &invlb1);
+                                table_get_msc_at(p, cfg.energy_loss, material,
+                                    l0, &mu0, &invlb1);
                                 invlb1 *= density;
                         } else
                                 invlb1 = trk.step_invlb1;
@@ -642,8 +658,8 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                                 event = EVENT_LIMIT_ENERGY;
                         }
                 } else if (dX < EPSILON_X * Xtot) {
-                        k1 -= sgn * cel_energy_loss(p, scheme, material, k1) *
-                            dX;
+                        k1 -= sgn *
+                            cel_energy_loss_at(p, scheme, material, l0) * dX;
                         if ((cfg.event & EVENT_LIMIT_ENERGY) &&
                             (cfg.limit_energy > 0.)) {
                                 if (((cfg.direction == MODE_FORWARD) &&
@@ -657,12 +673,13 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                                 k1 = 0.;
                         }
                 } else {
-                        k1 = cel_kinetic_energy(p, scheme, material, X);
+                        k1 = cel_kinetic_energy_at(p, scheme, material,
+                            locate_near(p, Xcol, X, l0.i));
                 }
         } else if (scheme == MODE_STRAGGLED) {
                 double ratio;
-                step_fluctuate(p, cfg, trk, rng, state, material, Xtot, dX, &k1,
-                    &ratio);
+                step_fluctuate(p, cfg, trk, rng, state, material, kl, l0, Xtot,
+                    dX, &k1, &ratio);
                 dk = fabs(state.energy - k1);
 
                 double kinetic_limit = -1.;
@@ -696,21 +713,22 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                 double k_x = -1.;
 
                 do {
-                        double xs_del =
-                            del_cross_section(p, material, state.energy);
-                        const double tmp_del =
-                            del_cross_section(p, material, k1);
+                        double xs_del = del_cross_section_at(p, material, l0);
+                        const double tmp_del = del_cross_section_at(
+                            p, material, klocate(p, kl, k1));
                         if (tmp_del > xs_del) xs_del = tmp_del;
                         if (xs_del <= 0.) break;
-                        const double X_del = -log(rng.uniform()) / xs_del;
+                        const double X_del = -xlog(rng.uniform()) / xs_del;
                         if (X_del >= Xmax) break;
-                        const double k_h = cel_kinetic_energy(
-                            p, scheme, material, Xtot - sgn * X_del);
+                        const double k_h = cel_kinetic_energy_at(p, scheme,
+                            material,
+                            locate_near(p, Xcol, Xtot - sgn * X_del, l0.i));
                         const double k_del = state.energy -
                             sgn * ratio * fabs(state.energy - k_h);
                         if (k_del <= 0.) break;
-                        const double r =
-                            del_cross_section(p, material, k_del) / xs_del;
+                        const double r = del_cross_section_at(p, material,
+                                             klocate(p, kl, k_del)) /
+                            xs_del;
                         if (rng.uniform() > r) break;
                         k_x = k_del;
                         Xmax = X_del;
@@ -729,19 +747,22 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                                         kmin = kmax, kmax = tmp;
                                 }
                                 (void)kmax;
-                                const double lb_ehs =
-                                    coulomb_ehs_length(p, material, kmin);
+                                const double lb_ehs = coulomb_ehs_length_at(
+                                    p, material, klocate(p, kl, kmin));
                                 if (lb_ehs <= 0.) break;
                                 const double X_ehs =
-                                    -log(rng.uniform()) * lb_ehs;
+                                    -xlog(rng.uniform()) * lb_ehs;
                                 if (X_ehs >= Xmax) break;
-                                const double k_h = cel_kinetic_energy(
-                                    p, scheme, material, Xtot - sgn * X_ehs);
+                                const double k_h = cel_kinetic_energy_at(p,
+                                    scheme, material,
+                                    locate_near(
+                                        p, Xcol, Xtot - sgn * X_ehs, l0.i));
                                 const double k_ehs = state.energy -
                                     sgn * ratio * fabs(state.energy - k_h);
                                 if (k_ehs <= 0.) break;
                                 const double r =
-                                    coulomb_ehs_length(p, material, k_ehs) /
+                                    coulomb_ehs_length_at(p, material,
+                                        klocate(p, kl, k_ehs)) /
                                     lb_ehs;
                                 if ((r <= 0.) || (rng.uniform() > 1. / r))
                                         break;
@@ -779,9 +800,13 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                 if (!(event & EVENT_LIMIT_ENERGY)) {
                         if (scheme <= MODE_MIXED) {
                                 if (scheme != MODE_DISABLED)
-                                        k1 = cel_kinetic_energy(p, scheme,
+                                        k1 = cel_kinetic_energy_at(p, scheme,
                                             material,
-                                            Xtot - sgn * (state.grammage - Xi));
+                                            locate_near(p, Xcol,
+                                                Xtot -
+                                                    sgn *
+                                                        (state.grammage - Xi),
+                                                l0.i));
                                 event = trk.step_foreseen;
                         } else if (!(event &
                                        (EVENT_VERTEX_COULOMB |
@@ -897,11 +922,12 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                 if (state.energy <= 0.) {
                         trk.step_invlb1 = invlb1;
                 } else {
-                        table_get_msc(p, cfg.energy_loss, material,
-                            state.energy, &mu0, &invlb1_);
+                        table_get_msc_at(p, cfg.energy_loss, material,
+                            klocate(p, kl, state.energy), &mu0, &invlb1_);
                         trk.step_invlb1 = locals.density * invlb1_;
                 }
         }
+        trk.iK = kl.hint;
 
         /* End of step magnetic field. */
         double rLarmor1 = 0., uT1[3] = { 0., 0., 0. };
@@ -954,8 +980,8 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                     (rLarmor1 > 0.) ? state.charge * step / rLarmor1 : 0.;
                 double theta = 0.5 * (theta0 + theta1);
                 if (cfg.direction == MODE_BACKWARD) theta = -theta;
-                double c = cos(theta);
-                double s = sin(theta);
+                double c = xcos(theta);
+                double s = xsin(theta);
                 double v[3];
                 int i;
                 for (i = 0; i < 3; i++) v[i] = 0.5 * (uT0[i] + uT1[i]);
@@ -982,7 +1008,7 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                 if (ilb1 > 1.) ilb1 = 1.;
                 double mu;
                 do {
-                        mu = -ilb1 * log(rng.uniform());
+                        mu = -ilb1 * xlog(rng.uniform());
                 } while (mu > 1.);
                 step_rotate_direction(rng, state, mu);
         }
@@ -1069,9 +1095,9 @@ PB_FN int stepping_begin(const Physics & p, const Settings & cfg,
         lp.wi = state.weight;
         lp.Xi = state.grammage;
         if (scheme > MODE_DISABLED) {
-                const double ki = state.energy;
-                lp.Xf = cel_grammage(p, scheme, lp.material, ki);
-                lp.dei = 1. / cel_energy_loss(p, scheme, lp.material, ki);
+                const Loc li = locate_near(p, p.K, state.energy, trk.iK);
+                lp.Xf = cel_grammage_at(p, scheme, lp.material, li);
+                lp.dei = 1. / cel_energy_loss_at(p, scheme, lp.material, li);
         } else {
                 lp.Xf = lp.dei = 0.;
         }
@@ -1127,9 +1153,9 @@ PB_FN int stepping_rearm(const Physics & p, const Settings & cfg,
         lp.wi = state.weight;
         lp.Xi = state.grammage;
         if (cfg.energy_loss >= MODE_CSDA) {
-                const double ki = state.energy;
-                lp.Xf = cel_grammage(p, scheme, lp.material, ki);
-                lp.dei = 1. / cel_energy_loss(p, scheme, lp.material, ki);
+                const Loc li = locate_near(p, p.K, state.energy, trk.iK);
+                lp.Xf = cel_grammage_at(p, scheme, lp.material, li);
+                lp.dei = 1. / cel_energy_loss_at(p, scheme, lp.material, li);
         }
         transport_limit(p, cfg, trk, rng, state, lp.material, lp.Xi, lp.Xf,
             &lp.grammage_max);
@@ -1168,12 +1194,13 @@ PB_FN int stepping_step(const Physics & p, const Settings & cfg,
         if ((cfg.direction == MODE_BACKWARD) &&
             (cfg.energy_loss >= MODE_CSDA)) {
                 const double wt = (cfg.decay == MODE_WEIGHTED) ?
-                    exp(-fabs(state.time - lp.ti) / p.ctau) :
+                    xexp(-fabs(state.time - lp.ti) / p.ctau) :
                     1.;
                 state.weight = lp.wi * wt * lp.dei *
-                    cel_energy_loss(p, scheme, lp.material, state.energy);
+                    cel_energy_loss_at(p, scheme, lp.material,
+                        locate_near(p, p.K, state.energy, trk.iK));
         } else if (cfg.decay == MODE_WEIGHTED) {
-                state.weight = lp.wi * exp(-fabs(state.time - lp.ti) / p.ctau);
+                state.weight = lp.wi * xexp(-fabs(state.time - lp.ti) / p.ctau);
         }
 
         if (trk.step_event &
@@ -1233,7 +1260,7 @@ template <class Rng>
 PB_FN int stepping_ehs(const Physics & p, const Settings & cfg,
     const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
 {
-        transport_do_ehs(p, cfg, rng, state, lp.material);
+        transport_do_ehs(p, cfg, rng, state, lp.material, trk.iK);
         if (cfg.event & trk.step_event) {
                 stepping_finish(cfg, state);
                 return PHASE_DONE;
@@ -1371,7 +1398,7 @@ PB_FN int transport_with_csda(const Physics & p, const Settings & cfg,
                 state.weight *= cel_energy_loss(p, MODE_CSDA, material, kf) /
                     cel_energy_loss(p, MODE_CSDA, material, ki);
         if (cfg.decay == MODE_WEIGHTED)
-                state.weight *= exp(-fabs(ti - state.time) / p.ctau);
+                state.weight *= xexp(-fabs(ti - state.time) / p.ctau);
 
         double path;
         if (cfg.direction == MODE_FORWARD)
@@ -1430,6 +1457,7 @@ PB_FN int track_begin(const Physics & p, const Settings & cfg,
         trk.randn_next = 0.;
         trk.error = RETURN_SUCCESS;
         trk.n_steps = 0;
+        trk.iK = p.n_energies / 2;
 
         if (state.decayed) {
                 out.event = EVENT_VERTEX_DECAY;
@@ -1471,7 +1499,7 @@ PB_FN int track_begin(const Physics & p, const Settings & cfg,
 
         if (cfg.decay == MODE_RANDOMISED) {
                 const double u = rng.uniform();
-                trk.lifetime = state.time - p.ctau * log(u);
+                trk.lifetime = state.time - p.ctau * xlog(u);
         }
 
         int do_stepping = 1;
