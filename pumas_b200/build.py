@@ -16,11 +16,13 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "-Xcompiler", "-ffp-contract=off", "--shared", "-cudart", "shared",
+    "--threads", "8",
 ]
 
 
 def sources():
-    return [os.path.join(CSRC, f) for f in ("kernels.cu", "cabi.cu")]
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))
+            if f.endswith(".cu")]
 
 
 def dependencies():

@@ -1024,7 +1024,8 @@ enum pumas_return pumas_b200_context_kernel_set(
                 return RAISE(pumas_b200_context_kernel_set,
                     PUMAS_RETURN_VALUE_ERROR, "no context (null)");
         if ((kernel != pb::KERNEL_WAVEFRONT) &&
-            (kernel != pb::KERNEL_MONOLITHIC))
+            (kernel != pb::KERNEL_MONOLITHIC) &&
+            (kernel != pb::KERNEL_WAVEFRONT_GENERAL))
                 return RAISE(pumas_b200_context_kernel_set,
                     PUMAS_RETURN_INDEX_ERROR, "invalid kernel index [%d]",
                     kernel);

@@ -14,8 +14,13 @@ namespace pb {
 constexpr int TRANSPORT_BLOCK = 128;
 
 enum {
-        KERNEL_WAVEFRONT = 0, /* persistent CTAs regrouping tracks by phase */
-        KERNEL_MONOLITHIC = 1 /* one thread runs one track to completion */
+        /* persistent warps regrouping tracks by phase; picks a specialised
+         * instantiation when one matches the settings */
+        KERNEL_WAVEFRONT = 0,
+        /* one thread runs one track to completion */
+        KERNEL_MONOLITHIC = 1,
+        /* the wavefront kernel, general instantiation only */
+        KERNEL_WAVEFRONT_GENERAL = 2
 };
 
 /* Size of the device scratch buffer launch_transport needs (work cursor and

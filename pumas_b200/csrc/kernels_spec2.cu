@@ -1,0 +1,13 @@
+/*
+ * kernels_spec2.cu -- wavefront kernel specialised at compile time for
+ * (STRAGGLED, DISABLED, FORWARD, WEIGHTED) in a single infinite medium without
+ * locals (examples/pumas/straight.c geometry). Same source as the general
+ * kernel (wavefront.cuh); only unreachable code is removed.
+ */
+#include "wavefront.cuh"
+
+namespace pb {
+
+PB_DEFINE_SPECIALISATION(launch_spec_straggled_noscat_forward, MODE_STRAGGLED, MODE_DISABLED, MODE_FORWARD, MODE_WEIGHTED)
+
+} /* namespace pb */

@@ -134,6 +134,40 @@ struct Settings {
         double accuracy;
 };
 
+/* The same settings with the four modes fixed at compile time: the transport
+ * functions are templates on the settings type and read `cfg.energy_loss` etc.
+ * either way, so a kernel instantiated on StaticSettings keeps only the code
+ * of its own configuration (no CSDA / mixed branches in a straggled kernel, no
+ * backward weights in a forward one ...). */
+template <int ENERGY_LOSS, int SCATTERING, int DIRECTION, int DECAY>
+struct StaticSettings {
+        static constexpr int energy_loss = ENERGY_LOSS;
+        static constexpr int decay = DECAY;
+        static constexpr int direction = DIRECTION;
+        static constexpr int scattering = SCATTERING;
+        int event;
+        double limit_energy;
+        double limit_distance;
+        double limit_grammage;
+        double limit_time;
+        double accuracy;
+
+        StaticSettings() = default;
+        PB_FN explicit StaticSettings(const Settings & s)
+            : event(s.event), limit_energy(s.limit_energy),
+              limit_distance(s.limit_distance),
+              limit_grammage(s.limit_grammage), limit_time(s.limit_time),
+              accuracy(s.accuracy)
+        {
+        }
+        PB_FN static bool matches(const Settings & s)
+        {
+                return (s.energy_loss == ENERGY_LOSS) &&
+                    (s.scattering == SCATTERING) &&
+                    (s.direction == DIRECTION) && (s.decay == DECAY);
+        }
+};
+
 } /* namespace pb */
 
 #endif

@@ -35,8 +35,8 @@ PB_FN double envelope_norm(double a, double xmin, double xmax)
 }
 
 /* pumas.c:6154-6270 */
-template <class Rng>
-PB_FN void del_randomise_target(const Physics & p, const Settings & cfg,
+template <class Cfg, class Rng>
+PB_FN void del_randomise_target(const Physics & p, const Cfg & cfg,
     Rng & rng, const State & state, int material, DelInfo * info)
 {
         int i1, i2;
@@ -138,8 +138,8 @@ PB_FN void del_randomise_target(const Physics & p, const Settings & cfg,
 
 /* pumas.c:5912-6017. Returns true when a polar angle must be sampled for
  * (*process, *element); false is the reference's NULL polar function. */
-template <class Rng>
-PB_FN bool del_randomise_forward(const Physics & p, const Settings & cfg,
+template <class Cfg, class Rng>
+PB_FN bool del_randomise_forward(const Physics & p, const Cfg & cfg,
     Rng & rng, State & state, int material, int * process, int * element)
 {
         if (state.energy <= p.Kt[material]) return false;
@@ -268,8 +268,8 @@ PB_FN void del_randomise_power_law(Rng & rng, double alpha, double xmin,
 }
 
 /* pumas.c:6036-6093 */
-template <class Rng>
-PB_FN bool del_randomise_reverse(const Physics & p, const Settings & cfg,
+template <class Cfg, class Rng>
+PB_FN bool del_randomise_reverse(const Physics & p, const Cfg & cfg,
     Rng & rng, State & state, int material, int * process, int * element)
 {
         const double lnq0 = -xlog(p.cutoff);

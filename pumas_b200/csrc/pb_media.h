@@ -94,6 +94,50 @@ PB_FN double set_locals(const Physics & p, const Geometry & g, double accuracy,
         return step_max * accuracy;
 }
 
+/* ---- compile time specialisation of the geometry ---------------------------
+ * The transport functions are templates on the geometry type. `Geometry` (the
+ * C descriptor) is the general, run time case. `UniformGeometry` is the same
+ * thing as a PUMAS_B200_GEOMETRY_UNIFORM descriptor whose single layer has no
+ * locals callback (examples/pumas/straight.c), with everything that cannot
+ * happen there (boundaries, density gradients, magnetic field) known at
+ * compile time, so that the kernels specialised for it carry none of that
+ * code. Results are identical to the general case. */
+struct UniformGeometry {
+        int material;
+        int step_type;
+};
+
+PB_FN int geo_material(const Geometry & g, int medium)
+{
+        return g.layer[medium].material;
+}
+PB_FN int geo_material(const UniformGeometry & g, int) { return g.material; }
+
+/* Can a step end in another medium? */
+PB_FN bool geo_has_boundaries(const Geometry &) { return true; }
+PB_FN constexpr bool geo_has_boundaries(const UniformGeometry &) { return false; }
+
+/* Can the locals (density, field) vary or the medium be magnetised? */
+PB_FN bool geo_has_locals(const Geometry &) { return true; }
+PB_FN constexpr bool geo_has_locals(const UniformGeometry &) { return false; }
+
+PB_FN int medium_locate(const UniformGeometry & g, int, const State &,
+    bool want_medium, int * medium, bool want_step, double * step_ptr)
+{
+        if (want_medium) *medium = 0;
+        if (want_step) *step_ptr = 0.;
+        return g.step_type;
+}
+
+PB_FN double set_locals(const Physics & p, const UniformGeometry & g, double,
+    int, const State &, Locals * locals)
+{
+        locals->density = p.material_density[g.material];
+        locals->magnet[0] = locals->magnet[1] = locals->magnet[2] = 0.;
+        locals->magnetized = 0;
+        return 0;
+}
+
 } /* namespace pb */
 
 #endif

@@ -122,8 +122,8 @@ PB_FN void step_rotate_direction(Rng & rng, State & state, double mu)
 /* PENELOPE style straggling of the continuous loss. pumas.c:6943-7005.
  * `l0` is the located start energy; the end energy of the continuous loss is
  * located through `kl`. */
-template <class Rng>
-PB_FN void step_fluctuate(const Physics & p, const Settings & cfg, Track & trk,
+template <class Cfg, class Rng>
+PB_FN void step_fluctuate(const Physics & p, const Cfg & cfg, Track & trk,
     Rng & rng, const State & state, int material, KLocator & kl, const Loc & l0,
     double Xtot, double dX, double * kf, double * ratio)
 {
@@ -182,8 +182,8 @@ PB_FN void step_fluctuate(const Physics & p, const Settings & cfg, Track & trk,
 }
 
 /* pumas.c:5569-5696 */
-template <class Rng>
-PB_FN void transport_limit(const Physics & p, const Settings & cfg, Track & trk,
+template <class Cfg, class Rng>
+PB_FN void transport_limit(const Physics & p, const Cfg & cfg, Track & trk,
     Rng & rng, const State & state, int material, double Xi, double Xf,
     double * grammage_max)
 {
@@ -289,8 +289,8 @@ PB_FN void transport_limit(const Physics & p, const Settings & cfg, Track & trk,
 }
 
 /* pumas.c:5706-5757 */
-template <class Rng>
-PB_FN void transport_do_del(const Physics & p, const Settings & cfg,
+template <class Cfg, class Rng>
+PB_FN void transport_do_del(const Physics & p, const Cfg & cfg,
     Track & trk, Rng & rng, State & state, int material)
 {
         double ki, kf;
@@ -355,8 +355,8 @@ PB_NOINLINE double coulomb_cs_hard(const Physics & p, int component,
 }
 
 /* pumas.c:5768-5885 */
-template <class Rng>
-PB_FN void transport_do_ehs(const Physics & p, const Settings & cfg, Rng & rng,
+template <class Cfg, class Rng>
+PB_FN void transport_do_ehs(const Physics & p, const Cfg & cfg, Rng & rng,
     State & state, int material, int hint)
 {
         const double kinetic = state.energy;
@@ -444,9 +444,9 @@ PB_FN void transport_do_ehs(const Physics & p, const Settings & cfg, Rng & rng,
 
 /* One Monte Carlo step in a single medium. pumas.c:6296-6925. Returns false
  * on error (trk.error set). */
-template <class Rng>
-PB_FN bool step_transport(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Track & trk, Rng & rng, State & state, int straight,
+template <class Cfg, class Geo, class Rng>
+PB_FN bool step_transport(const Physics & p, const Cfg & cfg,
+    const Geo & geo, Track & trk, Rng & rng, State & state, int straight,
     int medium, Locals & locals, double grammage_max, double step_max_medium,
     int step_max_type, double * step_max_locals, int * out_medium)
 {
@@ -454,7 +454,7 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
         const int scheme = cfg.energy_loss;
         double * const direction = state.direction;
         double * const position = state.position;
-        const int material = geo.layer[medium].material;
+        const int material = geo_material(geo, medium);
         const double density = locals.density;
         const double density_i = 1. / density;
         const double momentum = sqrt(state.energy * (state.energy + 2. * p.mass));
@@ -494,7 +494,7 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
                         if (stepT < step_loc) step_loc = stepT;
                 }
 
-                if (locals.magnetized == 0) {
+                if (!geo_has_locals(geo) || (locals.magnetized == 0)) {
                         rLarmor0 = 0.;
                 } else {
                         const double * const B = locals.magnet;
@@ -553,7 +553,7 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
         int end_medium = -1;
         medium_locate(geo, cfg.direction, state, true, &end_medium, false, 0);
         double end_position[3] = { position[0], position[1], position[2] };
-        if (end_medium != medium) {
+        if (geo_has_boundaries(geo) && (end_medium != medium)) {
                 if (step_max_type == STEP_CHECK) {
                         const double step_min =
                             (step < STEP_MIN) ? step : STEP_MIN;
@@ -610,12 +610,12 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
 
         /* End step locals. */
         double Bi[3] = { 0., 0., 0. };
-        if (locals.magnetized != 0) {
+        if (geo_has_locals(geo) && (locals.magnetized != 0)) {
                 Bi[0] = locals.magnet[0];
                 Bi[1] = locals.magnet[1];
                 Bi[2] = locals.magnet[2];
         }
-        if ((*step_max_locals > 0.) &&
+        if (geo_has_locals(geo) && (*step_max_locals > 0.) &&
             ((step_max_type != STEP_RAW) || (event != EVENT_MEDIUM))) {
                 *step_max_locals =
                     set_locals(p, geo, cfg.accuracy, medium, state, &locals);
@@ -931,7 +931,7 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
 
         /* End of step magnetic field. */
         double rLarmor1 = 0., uT1[3] = { 0., 0., 0. };
-        if (locals.magnetized) {
+        if (geo_has_locals(geo) && locals.magnetized) {
                 double B[3] = { locals.magnet[0], locals.magnet[1],
                         locals.magnet[2] };
                 int magnetized = locals.magnetized;
@@ -971,7 +971,7 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
         }
 
         /* Magnetic deflection. */
-        if ((rLarmor0 > 0.) || (rLarmor1 > 0.)) {
+        if (geo_has_locals(geo) && ((rLarmor0 > 0.) || (rLarmor1 > 0.))) {
                 const double u[3] = { direction[0], direction[1],
                         direction[2] };
                 const double theta0 =
@@ -1016,8 +1016,9 @@ PB_FN bool step_transport(const Physics & p, const Settings & cfg,
         return true;
 }
 
+template <class Cfg>
 PB_FN int straight_flag(
-    const Settings & cfg, double step_max_locals, const Locals & locals)
+    const Cfg & cfg, double step_max_locals, const Locals & locals)
 {
         return ((cfg.scattering == MODE_DISABLED) &&
                    (cfg.energy_loss <= MODE_MIXED) && (step_max_locals <= 0.) &&
@@ -1063,7 +1064,8 @@ struct Loop {
 };
 
 /* pumas.c:5492-5513 */
-PB_FN void stepping_finish(const Settings & cfg, State & state)
+template <class Cfg>
+PB_FN void stepping_finish(const Cfg & cfg, State & state)
 {
         if (cfg.direction == MODE_FORWARD) {
                 const double kinetic_min =
@@ -1081,11 +1083,11 @@ PB_FN void stepping_finish(const Settings & cfg, State & state)
 /* pumas.c:5210-5273. Returns PHASE_STEP, or PHASE_DONE when the track stops
  * before its first step (then `*final` tells whether the final protections
  * apply: the reference returns early, skipping them, at :5250-5273). */
-template <class Rng>
-PB_FN int stepping_begin(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+template <class Cfg, class Geo, class Rng>
+PB_FN int stepping_begin(const Physics & p, const Cfg & cfg,
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp)
 {
-        lp.material = geo.layer[lp.medium].material;
+        lp.material = geo_material(geo, lp.medium);
         const int scheme = cfg.energy_loss;
         lp.straight = straight_flag(cfg, lp.step_max_locals, lp.locals);
         lp.first = 1;
@@ -1135,12 +1137,12 @@ PB_FN int stepping_begin(const Physics & p, const Settings & cfg,
 
 /* pumas.c:5404-5416 and 5476-5488: refresh the locals after a vertex, update
  * the initial conditions and draw the next limits. */
-template <class Rng>
-PB_FN int stepping_rearm(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp,
+template <class Cfg, class Geo, class Rng>
+PB_FN int stepping_rearm(const Physics & p, const Cfg & cfg,
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp,
     bool after_vertex)
 {
-        if (after_vertex && (lp.step_max_locals > 0.)) {
+        if (geo_has_locals(geo) && after_vertex && (lp.step_max_locals > 0.)) {
                 lp.step_max_locals = set_locals(
                     p, geo, cfg.accuracy, lp.medium, state, &lp.locals);
                 if (lp.locals.density <= 0.) {
@@ -1168,9 +1170,9 @@ PB_FN int stepping_rearm(const Physics & p, const Settings & cfg,
 
 /* One iteration of the stepping loop, pumas.c:5277-5335 and, for a change of
  * medium, 5417-5467 + re-arm. */
-template <class Rng>
-PB_FN int stepping_step(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+template <class Cfg, class Geo, class Rng>
+PB_FN int stepping_step(const Physics & p, const Cfg & cfg,
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp)
 {
         if (!lp.first) {
                 lp.step_max_type = medium_locate(geo, cfg.direction, state,
@@ -1214,12 +1216,16 @@ PB_FN int stepping_step(const Physics & p, const Settings & cfg,
         }
 
         /* EVENT_MEDIUM */
+        if (!geo_has_boundaries(geo)) {
+                stepping_finish(cfg, state); /* not reached */
+                return PHASE_DONE;
+        }
         lp.medium = new_medium;
         if ((lp.medium < 0) || (cfg.event & EVENT_MEDIUM)) {
                 stepping_finish(cfg, state);
                 return PHASE_DONE;
         }
-        lp.material = geo.layer[lp.medium].material;
+        lp.material = geo_material(geo, lp.medium);
         lp.locals.density = 0.;
         lp.locals.magnet[0] = lp.locals.magnet[1] = lp.locals.magnet[2] = 0.;
         lp.locals.magnetized = 0;
@@ -1241,9 +1247,9 @@ PB_FN int stepping_step(const Physics & p, const Settings & cfg,
 }
 
 /* A hard inelastic event, pumas.c:5340-5392 then re-arm. */
-template <class Rng>
-PB_FN int stepping_del(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+template <class Cfg, class Geo, class Rng>
+PB_FN int stepping_del(const Physics & p, const Cfg & cfg,
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp)
 {
         transport_do_del(p, cfg, trk, rng, state, lp.material);
         if ((cfg.event & trk.step_event) || trk.step_event == EVENT_WEIGHT) {
@@ -1256,9 +1262,9 @@ PB_FN int stepping_del(const Physics & p, const Settings & cfg,
 }
 
 /* A hard elastic event, pumas.c:5393-5402 then re-arm. */
-template <class Rng>
-PB_FN int stepping_ehs(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+template <class Cfg, class Geo, class Rng>
+PB_FN int stepping_ehs(const Physics & p, const Cfg & cfg,
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp)
 {
         transport_do_ehs(p, cfg, rng, state, lp.material, trk.iK);
         if (cfg.event & trk.step_event) {
@@ -1269,11 +1275,12 @@ PB_FN int stepping_ehs(const Physics & p, const Settings & cfg,
 }
 
 /* Closed form CSDA in a uniform, field free medium. pumas.c:4777-4949. */
-PB_FN int transport_with_csda(const Physics & p, const Settings & cfg,
-    const Geometry & geo, const Track & trk, State & state, int medium,
+template <class Cfg, class Geo>
+PB_FN int transport_with_csda(const Physics & p, const Cfg & cfg,
+    const Geo & geo, const Track & trk, State & state, int medium,
     const Locals & locals)
 {
-        const int material = geo.layer[medium].material;
+        const int material = geo_material(geo, medium);
         const double density = locals.density;
         const double ki = state.energy;
         const double di = state.distance;
@@ -1420,7 +1427,8 @@ struct Outcome {
 };
 
 /* Batch level validation, pumas.c:3152-3177 (done once on the host). */
-PB_FN int settings_check(const Physics & p, const Settings & cfg)
+template <class Cfg>
+PB_FN int settings_check(const Physics & p, const Cfg & cfg)
 {
         if ((p.particle == 1) && (cfg.direction == MODE_FORWARD) &&
             (cfg.decay == MODE_WEIGHTED))
@@ -1438,9 +1446,9 @@ PB_FN int settings_check(const Physics & p, const Settings & cfg)
  * (the track is then over) or the prologue of the stepping. Returns the phase
  * of the track; `out` holds rc, the first medium and, when PHASE_DONE is
  * returned, the end event and last medium. */
-template <class Rng>
-PB_FN int track_begin(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Rng & rng, State & state, Track & trk, Loop & lp,
+template <class Cfg, class Geo, class Rng>
+PB_FN int track_begin(const Physics & p, const Cfg & cfg,
+    const Geo & geo, Rng & rng, State & state, Track & trk, Loop & lp,
     Outcome & out)
 {
         out.rc = RETURN_SUCCESS;
@@ -1547,9 +1555,9 @@ PB_FN void track_end(const Track & trk, const Loop & lp, Outcome & out)
 
 /* pumas_context_transport for one track run to completion (CPU build and the
  * reference kernel): the phases chained in sequence. */
-template <class Rng>
-PB_FN Outcome transport_track(const Physics & p, const Settings & cfg,
-    const Geometry & geo, Rng & rng, State & state, unsigned int * n_steps)
+template <class Cfg, class Geo, class Rng>
+PB_FN Outcome transport_track(const Physics & p, const Cfg & cfg,
+    const Geo & geo, Rng & rng, State & state, unsigned int * n_steps)
 {
         Outcome out;
         Track trk;
