@@ -1,0 +1,336 @@
+#!/usr/bin/env python3
+"""Benchmark of the transport hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+Workload ("headline"): forward transport of 1 TeV muons
+through 1 km of standard rock, straggled energy loss + mixed scattering,
+distance limit. A "step" is one pass of pumas_context_transport_n over one
+batch of --tracks synthetic tracks per GPU. Tracks shard across ranks by
+contiguous track id ranges (weak scaling: per GPU work is fixed); the only
+exchange is one NCCL all-reduce per step of the tally vector (sum w, sum w^2,
+counts per energy bin), as in BASELINE.json's north_star.
+
+One JSON line is printed by rank 0:
+  value     whole-job tracks/s, inputs resident in HBM when the timed region
+            starts (device pointers through the C ABI), CUDA events, max over
+            ranks, barrier + synchronize on both sides;
+  e2e       the same metric through the same C-ABI call with HOST (pinned)
+            buffers: H2D of the states and D2H of states + events inside the
+            timed region;
+  roofline  FP64-pipe roofline of the transport kernel: algorithmic flop =
+            600 flop per Monte Carlo step x the steps the launch
+            executed (counted by the kernel), over the kernel's CUDA-event
+            duration, against the DFMA peak measured live on this GPU;
+  cpu_baseline  the reference itself (oracle/_ref, the unmodified src/pumas.c)
+            on all host cores, one context per thread, on a bounded sample of
+            the same workload (rank 0, N = 1 only).
+`--impl reference` times that CPU reference alone with the same JSON schema.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "transported muon tracks/sec (straggled + mixed scattering, 1 km rock)"
+UNIT = "tracks/s"
+WORKLOAD = ("headline: forward, straggled energy loss, mixed scattering, "
+            "StandardRock uniform, 1 TeV muons, distance limit 1000 m")
+FLOP_PER_STEP = 600.
+TALLY_BINS = 60
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tracks", type=int, default=1 << 21,
+                    help="tracks per step and per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=0,
+                    help="tracks of the CPU baseline sample (0: auto)")
+    ap.add_argument("--workload", default="headline")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,"
+              "clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", "-i", str(self.index),
+                     "--query-gpu=" + self.FIELDS,
+                     "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(float(s[0]) for s in self.samples if s[0].replace(
+            ".", "").isdigit())
+        mx = [float(s[1]) for s in self.samples if s[1].replace(
+            ".", "").isdigit()]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                 "sw_power_cap")
+        reasons = [n for k, n in enumerate(names) if any(
+            len(s) > 3 + k and s[3 + k].lower().startswith("active")
+            for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+def reference_rate(workload, n, threads):
+    """Tracks/s of the unmodified reference (oracle/_ref) on the host cores."""
+    import harness
+    from workloads import WORKLOADS
+    dump, builder, kwargs = WORKLOADS[workload]
+    oracle = harness.Oracle(dump)
+    w = builder(oracle.material, n, **kwargs)
+    out = oracle.transport(w["settings"], w["geometry"], w["states"], seed=1,
+                           threads=threads)
+    return n / out[5], float(out[3].mean())
+
+
+def run_reference(args):
+    """--impl reference: the CPU reference alone, same schema."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import harness
+    if not harness.have_oracle():
+        print(json.dumps({"impl": "reference", "unavailable":
+                          "oracle/_ref/libpumas_oracle.so is not built"}))
+        return
+    threads = os.cpu_count() or 1
+    # bounded sample: ~1.5 k tracks/s/core on this workload
+    n = args.cpu_sample or max(2000, 1200 * threads)
+    rates = []
+    for _ in range(args.warmup):
+        reference_rate(args.workload, max(200, n // 8), threads)
+    t0 = time.time()
+    for _ in range(args.steps):
+        rates.append(reference_rate(args.workload, n, threads)[0])
+    elapsed = time.time() - t0
+    value = n * args.steps / sum(n / r for r in rates)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "tracks_per_step": n,
+                   "note": "CPU reference: unmodified src/pumas.c, one "
+                           "pumas_context per thread, Philox callback"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads,
+                         "kind": "reference",
+                         "sample": "%d tracks per step" % n},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import harness
+    import pumas_b200 as pb
+    from workloads import WORKLOADS
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available() or not pb.device_available():
+        raise SystemExit("bench.py needs a B200: no usable CUDA device "
+                         "(there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(
+            "cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.tracks
+    dump, builder, kwargs = WORKLOADS[args.workload]
+    physics = pb.Physics(harness.dump_path(dump))
+    w = builder(physics.material_index, n, **kwargs)
+    stream = torch.cuda.current_stream()
+    ctx = pb.Context(physics, seed=2026)
+    ctx.configure(w["settings"])
+    ctx.geometry(w["geometry"])
+    ctx.stream(stream.cuda_stream)
+
+    # Inputs: pristine states in HBM (restored device-to-device before each
+    # step), and in pinned host memory for the end-to-end leg.
+    host = torch.from_numpy(
+        w["states"].view(np.uint8).reshape(n, 104).copy()).pin_memory()
+    pristine = host.cuda()
+    work = torch.empty_like(pristine)
+    events = torch.zeros(n, dtype=torch.int32, device="cuda")
+    tally = torch.zeros(4 + TALLY_BINS, dtype=torch.float64, device="cuda")
+    scratch = torch.zeros(pb.tally_scratch_bytes(TALLY_BINS), dtype=torch.uint8,
+                          device="cuda")
+    from pumas_b200.sharding import allreduce_tallies, step_offset
+
+    def step(k):
+        """One pass of the hot path over this rank's batch, HBM resident."""
+        work.copy_(pristine, non_blocking=True)
+        ctx.track_offset(step_offset(k, rank, world, n))
+        ctx.transport_device(n, work.data_ptr(), events.data_ptr())
+        pb.tally(work.data_ptr(), events.data_ptr(), n,
+                 pb.EVENT_LIMIT_DISTANCE, 1e-3, 1e3, TALLY_BINS,
+                 tally.data_ptr(), scratch.data_ptr(), stream.cuda_stream)
+        allreduce_tallies(tally)
+        return ctx.last_kernel_time()
+
+    for k in range(args.warmup):
+        step(k)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    kernel_ms, launches, steps_total = 0., 0, 0
+    barrier()
+    e0.record()
+    for k in range(args.steps):
+        ms, nl = step(args.warmup + k)
+        kernel_ms += ms
+        launches += nl + 2  # transport kernel + the two tally kernels
+    e1.record()
+    barrier()
+    sampler.stop_flag.set()
+    elapsed_ms = e0.elapsed_time(e1)
+    nrand, nsteps = ctx.last_counters(n)
+    steps_per_track = float(nsteps.mean())
+    survival = float(tally[3].item() / tally[2].item()) if tally[2].item() else 0.
+
+    # End to end: host (pinned) buffers through the same C-ABI call.
+    host_np = host.numpy().reshape(-1).view(pb.STATE_DTYPE)
+    e2e_buf = torch.empty_like(host).pin_memory()
+    e2e_np = e2e_buf.numpy().reshape(-1).view(pb.STATE_DTYPE)
+    host_events = torch.zeros(n, dtype=torch.int32).pin_memory()
+
+    def e2e_step(k):
+        e2e_np[:] = host_np
+        ctx.track_offset(step_offset(k, rank, world, n))
+        t0 = time.perf_counter()
+        ctx.transport(e2e_np, host_events.numpy(), media=False)
+        return time.perf_counter() - t0
+
+    e2e_step(0)
+    barrier()
+    e2e_steps = max(2, args.steps // 2)
+    e2e_seconds = 0.
+    for k in range(e2e_steps):
+        e2e_seconds += e2e_step(100 + k)
+    barrier()
+
+    times = torch.tensor([elapsed_ms, e2e_seconds, kernel_ms],
+                         dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    elapsed_ms, e2e_seconds, kernel_ms = [float(x) for x in times.tolist()]
+
+    if rank == 0:
+        value = world * n * args.steps / (elapsed_ms * 1e-3)
+        e2e_value = world * n * e2e_steps / e2e_seconds
+        peak = pb.fp64_peak()
+        flop_per_launch = FLOP_PER_STEP * steps_per_track * n
+        achieved = flop_per_launch / (kernel_ms / args.steps * 1e-3) * 1e-12
+        cpu = None
+        if (world == 1) and harness.have_oracle():
+            threads = os.cpu_count() or 1
+            sample = args.cpu_sample or max(2000, 1500 * threads)
+            rate, _ = reference_rate(args.workload, sample, threads)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads,
+                   "kind": "reference",
+                   "sample": "%d tracks of the same workload, reference "
+                             "src/pumas.c, one context per thread" % sample}
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                t = json.load(open(tpath))
+                traffic = t["dram_bytes_per_track"] * n
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic",
+            "config": {
+                "workload": WORKLOAD, "tracks_per_step_per_gpu": n,
+                "steps_per_track": steps_per_track,
+                "survival_fraction": survival,
+                "l2": "inputs %d MB per step and per GPU (%s the 126 MB L2)" % (
+                    n * 104 >> 20,
+                    "larger than" if n * 104 > 126 << 20 else "NOT larger than"),
+                "sharding": "contiguous track id ranges per rank, one NCCL "
+                            "all-reduce of %d tally doubles per step" % (
+                                4 + TALLY_BINS),
+                "rng": "Philox4x32-10 keyed by (seed, track id)"},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": n * 104,
+                    "d2h_bytes_per_step": n * 108},
+            "gpu_launches": launches,
+            "roofline": {
+                "bound": "fp64", "achieved": achieved, "peak": peak,
+                "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+                "traffic": traffic,
+                "note": "algorithmic flop = %.0f flop/step x %.1f steps/track "
+                        "x %d tracks per launch; peak = DFMA peak measured "
+                        "live (pumas_b200_fp64_peak); HBM is not the bound: "
+                        "%.0f B/track algorithmic" % (
+                            FLOP_PER_STEP, steps_per_track, n, 212.)},
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

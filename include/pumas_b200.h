@@ -429,6 +429,23 @@ PUMAS_API void pumas_version(int * major, int * minor, int * patch);
 PUMAS_API enum pumas_return pumas_constant(
     enum pumas_constant index, double * value);
 
+/* New: tallies of a transported batch, on the device (what the user loop of
+ * examples/pumas/straight.c:175-178 accumulates per track). `states` and
+ * `events` are device pointers. `out` (device, 4 + n_bins doubles) receives
+ * [sum w, sum w^2, n, n selected, counts per log-spaced energy bin ...] over the
+ * tracks whose end event intersects `event_mask` (0 = all); reduction order is
+ * fixed, so results are reproducible. These are the values the ranks of a
+ * multi-GPU run all-reduce. */
+PUMAS_API long pumas_b200_tally_scratch_bytes(int n_bins);
+PUMAS_API enum pumas_return pumas_b200_tally(const struct pumas_state * states,
+    const int * events, long n, int event_mask, double energy_min,
+    double energy_max, int n_bins, double * out, void * scratch,
+    void * cuda_stream);
+
+/* New: measured FP64 FMA throughput of the current device, in TFLOP/s (the
+ * denominator of the roofline fraction reported by bench.py). */
+PUMAS_API enum pumas_return pumas_b200_fp64_peak(double * tflops);
+
 /* New: 1 when a CUDA device with compute capability 10.x is usable. */
 PUMAS_API int pumas_b200_device_available(void);
 

@@ -256,6 +256,18 @@ int oracle_transport_n(const struct pumas_physics * physics,
         return rc;
 }
 
+/* The Philox stream as the reference's random callback sees it. */
+void oracle_philox_uniforms(uint64_t seed, uint64_t track, int n, double * out)
+{
+        struct pumas_context context;
+        struct oracle_user_data u;
+        memset(&context, 0x0, sizeof context);
+        context.user_data = &u;
+        pb_philox_init(&u.rng, seed, track);
+        int i;
+        for (i = 0; i < n; i++) out[i] = oracle_random(&context);
+}
+
 /* Load a physics dump by path (ctypes has no FILE *). */
 int oracle_physics_load(struct pumas_physics ** physics, const char * path)
 {

@@ -60,16 +60,21 @@ struct Job {
         int rc;
 };
 
-void * worker(void * arg)
+/* 1: use the compile time specialised instantiations the GPU library uses
+ * (pumas_b200/csrc/kernels_spec*.cu) when the configuration matches; 0: the
+ * general instantiation only. */
+int g_specialise = 1;
+
+template <class Cfg, class Geo>
+void run_tracks(Job * job, const Cfg & cfg, const Geo & geo)
 {
-        Job * job = static_cast<Job *>(arg);
         const pb::Physics & p = job->hp->view;
         for (long i = job->begin; i < job->end; i++) {
                 PhiloxRng rng;
                 pb_philox_init(&rng.g, job->seed, job->offset + (uint64_t)i);
                 unsigned int steps = 0;
                 const pb::Outcome out = pb::transport_track(
-                    p, job->cfg, *job->geo, rng, job->states[i], &steps);
+                    p, cfg, geo, rng, job->states[i], &steps);
                 if ((out.rc != 0) && (job->rc == 0)) job->rc = out.rc;
                 if (job->events) job->events[i] = out.event;
                 if (job->media) {
@@ -79,12 +84,45 @@ void * worker(void * arg)
                 if (job->n_random) job->n_random[i] = rng.g.count;
                 if (job->n_steps) job->n_steps[i] = steps;
         }
+}
+
+template <int EL, int SC, int DI, int DE> bool try_specialised(Job * job)
+{
+        typedef pb::StaticSettings<EL, SC, DI, DE> Cfg;
+        const pumas_b200_geometry & geo = *job->geo;
+        if (!Cfg::matches(job->cfg) ||
+            (geo.kind != PUMAS_B200_GEOMETRY_UNIFORM) || geo.layer[0].has_locals)
+                return false;
+        pb::UniformGeometry ug;
+        ug.material = geo.layer[0].material;
+        ug.step_type = geo.step_type;
+        run_tracks(job, Cfg(job->cfg), ug);
+        return true;
+}
+
+void * worker(void * arg)
+{
+        Job * job = static_cast<Job *>(arg);
+        using namespace pb;
+        if (g_specialise &&
+            (try_specialised<MODE_STRAGGLED, MODE_MIXED, MODE_FORWARD,
+                 MODE_WEIGHTED>(job) ||
+                try_specialised<MODE_STRAGGLED, MODE_MIXED, MODE_BACKWARD,
+                    MODE_WEIGHTED>(job) ||
+                try_specialised<MODE_STRAGGLED, MODE_DISABLED, MODE_FORWARD,
+                    MODE_WEIGHTED>(job) ||
+                try_specialised<MODE_STRAGGLED, MODE_DISABLED, MODE_BACKWARD,
+                    MODE_WEIGHTED>(job)))
+                return NULL;
+        run_tracks(job, job->cfg, *job->geo);
         return NULL;
 }
 
 } /* namespace */
 
 extern "C" {
+
+void port_set_specialise(int enable) { g_specialise = enable; }
 
 void * port_physics_load(const char * path)
 {
@@ -190,6 +228,23 @@ int port_coulomb_cs_hard(const void * physics, int material, int scheme,
                     p, p.comp_offset[material] + i, kinetic, mu0);
         return n;
 }
+
+/* Philox stream hooks (tests/test_philox.py). */
+void port_philox_block(const uint32_t * ctr, const uint32_t * key, uint32_t * out)
+{
+        pb_philox4x32_10(ctr, key, out);
+}
+
+void port_philox_uniforms(uint64_t seed, uint64_t track, int n, double * out)
+{
+        pb_philox g;
+        pb_philox_init(&g, seed, track);
+        for (int i = 0; i < n; i++) out[i] = pb_philox_uniform(&g);
+}
+
+/* Single precision libm restatements (tests/test_libm_float.py). */
+float port_logf(float x) { return pb::logf_libm(x); }
+float port_expf(float x) { return pb::expf_libm(x); }
 
 /* Raw table access, same names as oracle_table(). */
 const double * port_table(const void * physics, const char * name, long * length)

@@ -203,6 +203,13 @@ def library():
         ctypes.c_void_p]
     lib.pumas_b200_context_last_kernel_time.argtypes = [
         ctypes.POINTER(ContextStruct), c_double_p, c_int_p]
+    lib.pumas_b200_tally_scratch_bytes.restype = ctypes.c_long
+    lib.pumas_b200_tally_scratch_bytes.argtypes = [ctypes.c_int]
+    lib.pumas_b200_tally.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_int,
+        ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p]
+    lib.pumas_b200_fp64_peak.argtypes = [c_double_p]
     lib.pumas_error_handler_set.argtypes = [_HANDLER_T]
     lib.pumas_error_handler_set(_handler)
     _lib = lib
@@ -217,6 +224,26 @@ def _check(rc):
 
 def device_available():
     return bool(library().pumas_b200_device_available())
+
+
+def fp64_peak():
+    """Measured FP64 FMA peak of the current device, TFLOP/s."""
+    t = ctypes.c_double()
+    _check(library().pumas_b200_fp64_peak(ctypes.byref(t)))
+    return t.value
+
+
+def tally_scratch_bytes(n_bins):
+    return library().pumas_b200_tally_scratch_bytes(n_bins)
+
+
+def tally(states_ptr, events_ptr, n, event_mask, energy_min, energy_max,
+          n_bins, out_ptr, scratch_ptr, stream=0):
+    """pumas_b200_tally on device pointers (integers)."""
+    _check(library().pumas_b200_tally(
+        ctypes.c_void_p(states_ptr), ctypes.c_void_p(events_ptr), n,
+        event_mask, energy_min, energy_max, n_bins, ctypes.c_void_p(out_ptr),
+        ctypes.c_void_p(scratch_ptr), ctypes.c_void_p(stream)))
 
 
 _libc = ctypes.CDLL(None)
@@ -342,7 +369,7 @@ class Context:
             media = np.zeros((n, 2), dtype=np.int32)
         _check(library().pumas_context_transport_n(
             self._ptr, n, states.ctypes.data, events.ctypes.data,
-            media.ctypes.data))
+            None if media is False else media.ctypes.data))
         return events, media
 
     def transport_device(self, n, states_ptr, events_ptr=None, media_ptr=None):

@@ -148,6 +148,10 @@ PB_FN dd real_log(const dd & x) { return dd_log(x); }
 #if !defined(__CUDA_ARCH__)
 inline long double real_log(long double x) { return logl(x); }
 #endif
+#if defined(PB_FORCE_QUAD)
+extern "C" __float128 logq(__float128);
+inline __float128 real_log(__float128 x) { return logq(x); }
+#endif
 
 /* Coefficients of the pole reduction, pumas.c:355-379 (a, b, c). */
 template <class R> struct CoulombPoles {

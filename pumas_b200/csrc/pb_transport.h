@@ -34,6 +34,9 @@ namespace pb {
 /* Working precision of the Coulomb pole reduction (see pb_coulomb.h). */
 #if defined(__CUDA_ARCH__) || defined(PB_FORCE_DD)
 typedef dd CoulombReal;
+#elif defined(PB_FORCE_QUAD)
+/* (test only: IEEE binary128 as the yardstick for the two others) */
+typedef __float128 CoulombReal;
 #else
 typedef long double CoulombReal;
 #endif

@@ -1,0 +1,117 @@
+"""The host side of the C ABI (libpumas_b200.so): dump loader and property
+getters against the reference (oracle/_ref). No GPU needed: these entry points
+are host functions in the reference too (pumas.c:2049, 2854-3111)."""
+import ctypes
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+import harness
+import pumas_b200 as pb
+from harness import MODE_CSDA, MODE_DISABLED, MODE_MIXED
+
+
+@pytest.fixture(scope="module")
+def physics():
+    return pb.Physics(harness.dump_path())
+
+
+def test_dump_round_trip(physics, tmp_path):
+    out = tmp_path / "again.pumas"
+    physics.dump(str(out))
+    assert filecmp.cmp(str(out), harness.dump_path(), shallow=False)
+
+
+def test_particle_and_materials(physics, oracle):
+    kind, ctau, mass = physics.particle()
+    assert (kind, ctau, mass) == (0, 658.654, 0.10565839)
+    for name in ("StandardRock", "Water", "Air", "WetRock"):
+        assert physics.material_index(name) == oracle.material(name)
+    with pytest.raises(pb.PumasError) as e:
+        physics.material_index("Unobtainium")
+    assert e.value.rc == 22  # PUMAS_RETURN_UNKNOWN_MATERIAL
+
+
+def test_tau_dump():
+    tau = pb.Physics(harness.dump_path("ice.tau"))
+    kind, ctau, mass = tau.particle()
+    assert kind == 1 and ctau == 87.03e-6 and mass == 1.77682
+    assert tau.material_index("Ice") == 0
+
+
+def test_properties_bit_exact(physics, oracle):
+    """Every property getter, all materials, energies across and beyond the
+    grid: identical doubles."""
+    energies = np.concatenate([
+        np.exp(np.linspace(np.log(5e-4), np.log(5e9), 150)), [0., 1e-3, 1e9]])
+    cases = []
+    for m in range(4):
+        for k in energies:
+            k = float(k)
+            for mode in (MODE_CSDA, MODE_MIXED):
+                cases += [("range", mode, m, k), ("proper_time", mode, m, k),
+                          ("stopping_power", mode, m, k),
+                          ("kinetic_energy", mode, m, k * 1e3)]
+            cases += [("magnetic_rotation", m, k), ("energy_straggling", m, k),
+                      ("cross_section", m, k)]
+            if k > 0.:
+                cases += [("elastic_cutoff_angle", m, k), ("elastic_path", m, k)]
+                for mode in (MODE_DISABLED, MODE_CSDA, MODE_MIXED):
+                    cases.append(("transport_path", mode, m, k))
+    for name, *args in cases:
+        rc, expected = oracle.property(name, *args)
+        assert rc == 0
+        got = physics.property(name, *args)
+        assert got == expected or (np.isnan(got) and np.isnan(expected)), (
+            name, args, got, expected)
+
+
+def test_property_errors(physics):
+    with pytest.raises(pb.PumasError) as e:
+        physics.property("range", 2, 0, 1.)  # STRAGGLED is not a table scheme
+    assert e.value.rc == 7
+    with pytest.raises(pb.PumasError) as e:
+        physics.property("range", MODE_CSDA, 17, 1.)
+    assert e.value.rc == 7
+
+
+def test_load_errors(tmp_path):
+    bad = tmp_path / "bad.pumas"
+    bad.write_bytes(b"\x0c\x00\x00\x00" + b"\x00" * 64)  # tag 12
+    with pytest.raises(pb.PumasError) as e:
+        pb.Physics(str(bad))
+    assert e.value.rc == 11  # FORMAT_ERROR, pumas.c:2077
+    data = open(harness.dump_path(), "rb").read()
+    cut = tmp_path / "cut.pumas"
+    cut.write_bytes(data[:100000])
+    with pytest.raises(pb.PumasError) as e:
+        pb.Physics(str(cut))
+    assert e.value.rc == 10  # IO_ERROR: truncated
+
+
+def test_no_cpu_fallback(physics):
+    """Without a B200 the transport entry point fails loudly."""
+    if pb.device_available():
+        pytest.skip("a GPU is present")
+    ctx = pb.Context(physics)
+    ctx.geometry(pb.uniform_geometry(0))
+    with pytest.raises(pb.PumasError) as e:
+        ctx.transport(pb.make_states(3, 1.))
+    assert e.value.rc == 9  # PUMAS_RETURN_INTERNAL_ERROR
+
+
+def test_error_catch_and_raise(physics):
+    """pumas_error_catch / pumas_error_raise, pumas.c:2306-2327."""
+    lib = pb.library()
+    lib.pumas_error_catch(1)
+    i = ctypes.c_int()
+    rc = lib.pumas_physics_material_index(
+        physics._handle, b"Nope", ctypes.byref(i))
+    assert rc == 22
+    rc2 = lib.pumas_physics_material_index(
+        physics._handle, b"StandardRock", ctypes.byref(i))
+    assert rc2 == 0
+    assert lib.pumas_error_raise() == 22  # first caught error is re-raised
+    assert lib.pumas_error_raise() == 18  # RAISE_ERROR: nothing was caught
