@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3",
     "-std=c++17", "-fmad=false", "-Xcompiler", "-fPIC", "-Xcompiler", "-O2",
     "-Xcompiler", "-ffp-contract=off", "--shared", "-cudart", "shared",
-    "--threads", "8",
+    "--threads", "8", "-diag-suppress", "128",
 ]
 
 
@@ -40,12 +40,20 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in dependencies())
 
 
+def flags():
+    """NVCC_FLAGS with the PUMAS_B200_FMAD=1 override (tuning only)."""
+    out = list(NVCC_FLAGS)
+    if os.environ.get("PUMAS_B200_FMAD") == "1":
+        out[out.index("-fmad=false")] = "-fmad=true"
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return TARGET
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("PUMAS_B200_NVCC_EXTRA", "").split()
-    cmd = [nvcc] + NVCC_FLAGS + extra + [
+    cmd = [nvcc] + flags() + extra + [
         "-I", CSRC, "-I", os.path.join(ROOT, "include"), "-o", TARGET
     ] + sources()
     if verbose:

@@ -40,6 +40,22 @@ PB_MATH double xlog(double x) { return log(x); }
 PB_MATH double xexp(double x) { return exp(x); }
 PB_MATH double xsin(double x) { return sin(x); }
 PB_MATH double xcos(double x) { return cos(x); }
+/* sin and cos of the same argument. The device sincos() shares the argument
+ * reduction and returns the values sin() and cos() return. */
+struct SinCos {
+        double s, c;
+};
+PB_MATH SinCos xsincos(double x)
+{
+        SinCos r;
+#if defined(__CUDA_ARCH__)
+        sincos(x, &r.s, &r.c);
+#else
+        r.c = cos(x);
+        r.s = sin(x);
+#endif
+        return r;
+}
 PB_MATH double xatan(double x) { return atan(x); }
 PB_MATH double xacos(double x) { return acos(x); }
 PB_MATH double xlog10(double x) { return log10(x); }

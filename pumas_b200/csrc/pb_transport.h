@@ -64,10 +64,9 @@ template <class Rng> PB_FN double step_randn(Track & trk, Rng & rng)
 
         const double r = sqrt(-2. * xlog(rng.uniform()));
         const double phi = 2. * PI * rng.uniform();
-        const double c = xcos(phi);
-        const double s = xsin(phi);
-        trk.randn_next = r * c;
-        return r * s;
+        const SinCos sc = xsincos(phi);
+        trk.randn_next = r * sc.c;
+        return r * sc.s;
 }
 
 /* pumas.c:7042-7095 */
@@ -81,42 +80,32 @@ PB_FN void step_rotate_direction(Rng & rng, State & state, double mu)
         if (stsq <= 0.) return;
         const double st = sqrt(stsq);
 
-        double u0x = 0., u0y = 0., u0z = 0.;
+        /* Co-vector of the local basis, orthogonal to the direction and to the
+         * axis of its smallest component. Written without branches (the
+         * reference has four, pumas.c:7059-7083; same operands, same
+         * operations): lanes of a warp take all four cases. */
         const double a0 = fabs(direction[0]);
         const double a1 = fabs(direction[1]);
         const double a2 = fabs(direction[2]);
-        if (a0 > a1) {
-                if (a0 > a2) {
-                        const double nrm = 1. /
-                            sqrt(direction[0] * direction[0] +
-                                direction[2] * direction[2]);
-                        u0x = -direction[2] * nrm, u0z = direction[0] * nrm;
-                } else {
-                        const double nrm = 1. /
-                            sqrt(direction[1] * direction[1] +
-                                direction[2] * direction[2]);
-                        u0y = direction[2] * nrm, u0z = -direction[1] * nrm;
-                }
-        } else {
-                if (a1 > a2) {
-                        const double nrm = 1. /
-                            sqrt(direction[0] * direction[0] +
-                                direction[1] * direction[1]);
-                        u0x = direction[1] * nrm, u0y = -direction[0] * nrm;
-                } else {
-                        const double nrm = 1. /
-                            sqrt(direction[1] * direction[1] +
-                                direction[2] * direction[2]);
-                        u0y = direction[2] * nrm, u0z = -direction[1] * nrm;
-                }
-        }
+        const bool case_xz = (a0 > a1) && (a0 > a2);   /* uses (x, z) */
+        const bool case_xy = !(a0 > a1) && (a1 > a2);  /* uses (x, y) */
+        const double pa = (case_xz || case_xy) ? direction[0] : direction[1];
+        const double pb_ = case_xy ? direction[1] : direction[2];
+        const double nrm = 1. / sqrt(pa * pa + pb_ * pb_);
+        const double u0x = case_xz ? -direction[2] * nrm :
+            (case_xy ? direction[1] * nrm : 0.);
+        const double u0y = case_xz ? 0. :
+            (case_xy ? -direction[0] * nrm : direction[2] * nrm);
+        const double u0z = case_xz ? direction[0] * nrm :
+            (case_xy ? 0. : -direction[1] * nrm);
         const double u1x = u0y * direction[2] - u0z * direction[1];
         const double u1y = u0z * direction[0] - u0x * direction[2];
         const double u1z = u0x * direction[1] - u0y * direction[0];
 
         const double phi = PI * (1. - 2. * rng.uniform());
-        const double cp = xcos(phi);
-        const double sp = xsin(phi);
+        const SinCos sc = xsincos(phi);
+        const double cp = sc.c;
+        const double sp = sc.s;
         direction[0] = cos_theta * direction[0] + st * (cp * u0x + sp * u1x);
         direction[1] = cos_theta * direction[1] + st * (cp * u0y + sp * u1y);
         direction[2] = cos_theta * direction[2] + st * (cp * u0z + sp * u1z);
@@ -983,8 +972,9 @@ PB_FN bool step_transport(const Physics & p, const Cfg & cfg,
                     (rLarmor1 > 0.) ? state.charge * step / rLarmor1 : 0.;
                 double theta = 0.5 * (theta0 + theta1);
                 if (cfg.direction == MODE_BACKWARD) theta = -theta;
-                double c = xcos(theta);
-                double s = xsin(theta);
+                const SinCos sc = xsincos(theta);
+                double c = sc.c;
+                double s = sc.s;
                 double v[3];
                 int i;
                 for (i = 0; i < 3; i++) v[i] = 0.5 * (uT0[i] + uT1[i]);

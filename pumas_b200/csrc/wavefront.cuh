@@ -110,7 +110,7 @@ struct DeviceRng {
  * together and share its instruction cache lines, plus WF_DEL_WARPS warps that
  * serve the hard inelastic events of the whole CTA asynchronously. */
 #ifndef PB_WF_WARPS
-#define PB_WF_WARPS 12
+#define PB_WF_WARPS 16
 #endif
 #ifndef PB_WF_DEL_WARPS
 #define PB_WF_DEL_WARPS 1
@@ -126,8 +126,16 @@ constexpr int WF_SLOTS_MAX = 128; /* track slots per warp (upper bound) */
 constexpr int WF_CTAS_PER_SM = PB_WF_CTAS_PER_SM;
 /* Parked events are served once this many are pending, or earlier when the
  * warp cannot fill a stepping pass. */
-constexpr int WF_SLOTS_DEFAULT = 64;
+/* The stepping warps re-align (named barrier) every WF_SYNC_ROUNDS rounds: often
+ * enough to keep sharing instruction cache lines, seldom enough to average out
+ * the round to round variance of the slowest warp. */
+#ifndef PB_WF_SYNC_ROUNDS
+#define PB_WF_SYNC_ROUNDS 1
+#endif
+constexpr int WF_SYNC_ROUNDS = PB_WF_SYNC_ROUNDS;
+constexpr int WF_SLOTS_DEFAULT = 96;
 constexpr int WF_EHS_THRESHOLD = 16;
+constexpr int WF_EHS_PERIOD = 4;
 constexpr int WF_DEL_THRESHOLD = 8;
 /* Pool phases: PHASE_STEP, PHASE_EHS, PHASE_DEL (pb_transport.h), then */
 constexpr int PHASE_DELQ = 3;  /* hard inelastic event handed to a DEL warp */
@@ -354,6 +362,7 @@ struct WavefrontArgs {
         unsigned long long * stats; /* optional scheduler statistics */
         int slots;                  /* track slots per warp */
         int ehs_threshold;
+        int ehs_period; /* > 0: serve the elastic events every that many rounds */
         int del_threshold;
 };
 
@@ -495,8 +504,9 @@ __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM)
                 const unsigned int lt_mask = (1u << lane) - 1u;
                 bool exhausted = false;
                 bool counted = false;
+                unsigned int round = 0;
 
-                for (;;) {
+                for (;; round++) {
                         /* regroup the slots by pending work */
                         int count[N_PHASES];
 #pragma unroll
@@ -527,10 +537,12 @@ __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM)
                                 if (lane == 0)
                                         atomicAdd((unsigned int *)&sh.n_done, 1u);
                         }
-                        /* lockstep: every stepping warp starts its passes
-                         * together (and leaves together) */
-                        named_barrier_sync(1, 32 * WF_STEP_WARPS);
-                        if (sh.n_done == WF_STEP_WARPS) break;
+                        /* lockstep: the stepping warps start their passes
+                         * together (and leave together) */
+                        if ((round % WF_SYNC_ROUNDS) == 0) {
+                                named_barrier_sync(1, 32 * WF_STEP_WARPS);
+                                if (sh.n_done == WF_STEP_WARPS) break;
+                        }
                         stat[STAT_ROUNDS]++;
 
                         /* refill the empty slots from the global cursor */
@@ -602,9 +614,19 @@ __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM)
                         }
 
                         /* hard elastic events */
+#if PB_WF_SYNC_ROUNDS == 1 && !defined(PB_WF_NO_EHS_BARRIER)
                         named_barrier_sync(3, 32 * WF_STEP_WARPS);
-                        if ((n_ehs >= a.ehs_threshold) ||
-                            ((n_ehs > 0) && (n_step < 32))) {
+#endif
+                        /* Served in the same rounds by every warp (lockstep:
+                         * a round lasts as long as its slowest warp), or
+                         * when the warp is running out of steps. */
+                        if ((n_ehs > 0) &&
+                            ((a.ehs_period > 0) ?
+                                    (((round % a.ehs_period) ==
+                                         (unsigned int)(a.ehs_period - 1)) ||
+                                        (n_step < 16)) :
+                                    ((n_ehs >= a.ehs_threshold) ||
+                                        (n_step < 32)))) {
                                 stat[STAT_EHS_PASSES] += (n_ehs + 31) / 32;
                                 stat[STAT_EHS_LANES] += n_ehs;
                                 for (int j = lane; j < n_ehs; j += 32) {
@@ -649,14 +671,14 @@ __global__ void __launch_bounds__(WF_THREADS, WF_CTAS_PER_SM)
 
 /* Scheduler tunables (environment overrides are for tuning runs). */
 struct WavefrontTunables {
-        int slots, ehs_threshold, del_threshold;
+        int slots, ehs_threshold, ehs_period, del_threshold;
         unsigned long long * stats;
         int sms;
 };
 
 inline const WavefrontTunables & wavefront_tunables()
 {
-        static WavefrontTunables t = { 0, 0, 0, nullptr, 0 };
+        static WavefrontTunables t = { 0, 0, 0, 0, nullptr, 0 };
         if (t.slots != 0) return t;
         const char * v;
         int slots = WF_SLOTS_DEFAULT;
@@ -667,6 +689,9 @@ inline const WavefrontTunables & wavefront_tunables()
                 t.ehs_threshold = atoi(v);
         if ((v = getenv("PUMAS_B200_WF_DEL")) != nullptr)
                 t.del_threshold = atoi(v);
+        t.ehs_period = WF_EHS_PERIOD;
+        if ((v = getenv("PUMAS_B200_WF_EHS_PERIOD")) != nullptr)
+                t.ehs_period = atoi(v);
         slots = ((slots + 31) / 32) * 32;
         if (slots < 32) slots = 32;
         if (slots > WF_SLOTS_MAX) slots = WF_SLOTS_MAX;
@@ -741,6 +766,7 @@ cudaError_t launch_wavefront(const Physics & p, const Cfg & cfg,
         a.stats = t.stats;
         a.slots = t.slots;
         a.ehs_threshold = t.ehs_threshold;
+        a.ehs_period = t.ehs_period;
         a.del_threshold = t.del_threshold;
         transport_wavefront_kernel<Cfg, Geo>
             <<<grid, WF_THREADS, smem, stream>>>(p, cfg, geo, a);
