@@ -26,6 +26,9 @@ N_TRACKS = {
     "mixed_loss_scattering": 2000, "mixed_loss_bwd": 4000,
     "geometry_detailed": 4000, "geometry_fast": 20000, "layers_check": 2000,
     "decay_randomised": 2000, "no_loss": 1500, "tau_ice": 20000,
+    "above_grid": 4000, "above_grid_mixed": 20000, "vertex_stop": 20000, "vertex_stop_bwd": 20000, "limits_all": 6000,
+    "limits_all_bwd": 6000, "limits_all_csda": 6000,
+    "limits_all_mixed_bwd": 6000,
 }
 # Largest tolerated fraction of tracks that do not meet RTOL: tracks whose
 # event sequence diverged (different number of variates or end event) plus

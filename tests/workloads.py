@@ -176,10 +176,51 @@ def tau_ice(material, n, seed=0):
     return dict(
         settings=make_settings(MODE_STRAGGLED, MODE_MIXED,
                                direction=MODE_BACKWARD, decay=MODE_WEIGHTED,
-                               event=EVENT_LIMIT_DISTANCE, limit_distance=10.),
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=300.),
         geometry=uniform_geometry(material("Ice")),
         states=make_states(n, log_uniform(n, 1e2, 1e6, seed), weight=1.,
                            direction=(0., 0., -1.)))
+
+
+def vertex_stop(material, n, seed=0, direction=MODE_FORWARD):
+    """Stop at the first vertex: every VERTEX bit in the event mask
+    (pumas.c:5377-5381, 5399-5401), wide energy range."""
+    from harness import EVENT_VERTEX_COULOMB, EVENT_VERTEX_DEL
+    return dict(
+        settings=make_settings(MODE_STRAGGLED, MODE_MIXED, direction=direction,
+                               event=(EVENT_VERTEX_DEL | EVENT_VERTEX_COULOMB |
+                                      EVENT_LIMIT_DISTANCE),
+                               limit_distance=2e3),
+        geometry=uniform_geometry(material("Water")),
+        states=make_states(n, log_uniform(n, 1e-2, 1e5, seed),
+                           direction=isotropic(n, seed + 1)))
+
+
+def limits_all(material, n, seed=0, direction=MODE_FORWARD,
+               energy_loss=MODE_STRAGGLED):
+    """Every external limit armed in the stepping engine, energies from just
+    above the first grid node up to 1 PeV, both directions."""
+    k = log_uniform(n, 2e-3, 1e6, seed)
+    return dict(
+        settings=make_settings(
+            energy_loss, MODE_MIXED, direction=direction,
+            event=(EVENT_LIMIT_DISTANCE | EVENT_LIMIT_GRAMMAGE |
+                   EVENT_LIMIT_ENERGY | EVENT_LIMIT_TIME),
+            limit_distance=80., limit_grammage=3e5,
+            limit_energy=(5e-2 if direction == MODE_FORWARD else 1e12),
+            limit_time=60.),
+        geometry=uniform_geometry(material("StandardRock")),
+        states=make_states(n, k[:n], direction=isotropic(n, seed + 1)))
+
+
+def above_grid(material, n, seed=0, energy_loss=MODE_STRAGGLED):
+    """Energies beyond the last grid node (1e9 GeV): the analytic
+    extrapolations of pumas.c:3651-3660, 3833-3838, 3901, no scattering."""
+    return dict(
+        settings=make_settings(energy_loss, MODE_DISABLED,
+                               event=EVENT_LIMIT_DISTANCE, limit_distance=10.),
+        geometry=uniform_geometry(material("StandardRock")),
+        states=make_states(n, log_uniform(n, 5e8, 1e11, seed)))
 
 
 # name -> (dump, builder, kwargs)
@@ -204,4 +245,18 @@ WORKLOADS = {
     "decay_randomised": ("materials.muon", decay_randomised, {}),
     "no_loss": ("materials.muon", no_loss, {}),
     "tau_ice": ("ice.tau", tau_ice, {}),
+    "vertex_stop": ("materials.muon", vertex_stop, {}),
+    "vertex_stop_bwd": ("materials.muon", vertex_stop,
+                        dict(direction=MODE_BACKWARD)),
+    "above_grid": ("materials.muon", above_grid, {}),
+    "above_grid_mixed": ("materials.muon", above_grid,
+                         dict(energy_loss=MODE_MIXED)),
+    "limits_all": ("materials.muon", limits_all, {}),
+    "limits_all_bwd": ("materials.muon", limits_all,
+                       dict(direction=MODE_BACKWARD)),
+    "limits_all_csda": ("materials.muon", limits_all,
+                        dict(energy_loss=MODE_CSDA)),
+    "limits_all_mixed_bwd": ("materials.muon", limits_all,
+                             dict(energy_loss=MODE_MIXED,
+                                  direction=MODE_BACKWARD)),
 }
