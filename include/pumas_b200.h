@@ -376,10 +376,11 @@ PUMAS_API enum pumas_return pumas_b200_context_track_offset_set(
 PUMAS_API enum pumas_return pumas_b200_context_stream_set(
     struct pumas_context * context, void * cuda_stream);
 
-/* New. Select the device kernel: 0 (default) the wavefront kernel, persistent
- * CTAs that regroup tracks by pending work; 1 the monolithic kernel, one thread
- * per track for its whole life (kept for A/B parity and profiling). Both give
- * the same per-track results. */
+/* New. Select the device kernel: 0 (default) the resident kernel, persistent
+ * CTAs whose lanes keep their track in registers and regroup tracks by pending
+ * event; 1 the monolithic kernel, one thread per track for its whole life
+ * (kept for A/B parity and profiling); 2 the resident kernel without compile
+ * time specialisation. All give the same per-track results. */
 PUMAS_API enum pumas_return pumas_b200_context_kernel_set(
     struct pumas_context * context, int kernel);
 

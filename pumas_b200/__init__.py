@@ -355,7 +355,8 @@ class Context:
             self._ptr, ctypes.c_void_p(cuda_stream)))
 
     def kernel(self, kernel):
-        """0: wavefront kernel (default), 1: monolithic kernel."""
+        """0: resident kernel (default), 1: monolithic kernel, 2: resident
+        kernel, general instantiation only."""
         _check(library().pumas_b200_context_kernel_set(self._ptr, kernel))
 
     def transport(self, states, events=None, media=None):

@@ -1023,9 +1023,8 @@ enum pumas_return pumas_b200_context_kernel_set(
         if (context == nullptr)
                 return RAISE(pumas_b200_context_kernel_set,
                     PUMAS_RETURN_VALUE_ERROR, "no context (null)");
-        if ((kernel != pb::KERNEL_WAVEFRONT) &&
-            (kernel != pb::KERNEL_MONOLITHIC) &&
-            (kernel != pb::KERNEL_WAVEFRONT_GENERAL))
+        if ((kernel < pb::KERNEL_RESIDENT) ||
+            (kernel > pb::KERNEL_RESIDENT_GENERAL))
                 return RAISE(pumas_b200_context_kernel_set,
                     PUMAS_RETURN_INDEX_ERROR, "invalid kernel index [%d]",
                     kernel);

@@ -1,8 +1,8 @@
 /*
  * kernels.cu -- the general transport kernels and the kernel dispatch.
  *
- *   transport_wavefront_kernel<Settings, Geometry>  (wavefront.cuh) the
- *     product path for any configuration;
+ *   transport_resident_kernel<Settings, Geometry>  (resident.cuh) the product
+ *     path for any configuration;
  *   specialised instantiations of the same template for the common
  *     configurations live in kernels_spec*.cu and are tried first;
  *   transport_kernel: one thread runs one track to completion; kept for A/B
@@ -11,7 +11,7 @@
  * The physics tables stay in HBM / L2 (1.6 MB) and are read through L1; a
  * track state crosses HBM twice (104 B in, 104 B out).
  */
-#include "wavefront.cuh"
+#include "resident.cuh"
 
 namespace pb {
 
@@ -51,7 +51,7 @@ PB_SPECIALISATION(launch_spec_straggled_noscat_backward);
 
 cudaError_t transport_workspace_bytes(size_t * bytes)
 {
-        *bytes = wavefront_workspace_bytes();
+        *bytes = workspace_bytes();
         return cudaSuccess;
 }
 
@@ -70,7 +70,7 @@ cudaError_t launch_transport(const Physics & p, const Settings & cfg,
                 return cudaGetLastError();
         }
 
-        if (kernel == KERNEL_WAVEFRONT) {
+        if (kernel == KERNEL_RESIDENT) {
                 cudaError_t e = cudaSuccess;
 #define TRY(NAME)                                                              \
         if (NAME(p, cfg, geo, seed, offset, n, states, events, media, status,  \
@@ -82,8 +82,8 @@ cudaError_t launch_transport(const Physics & p, const Settings & cfg,
                 TRY(launch_spec_straggled_noscat_backward)
 #undef TRY
         }
-        /* KERNEL_WAVEFRONT_GENERAL, or no specialisation applies. */
-        return launch_wavefront(p, cfg, geo, seed, offset, n, states, events,
+        /* KERNEL_RESIDENT_GENERAL, or no specialisation applies. */
+        return launch_resident(p, cfg, geo, seed, offset, n, states, events,
             media, status, n_random, n_steps, workspace, stream);
 }
 

@@ -14,17 +14,18 @@ namespace pb {
 constexpr int TRANSPORT_BLOCK = 128;
 
 enum {
-        /* persistent warps regrouping tracks by phase; picks a specialised
-         * instantiation when one matches the settings */
-        KERNEL_WAVEFRONT = 0,
+        /* persistent CTAs, one track per lane kept in registers, events
+         * regrouped through shared memory pools and queues (resident.cuh);
+         * picks a specialised instantiation when one matches the settings */
+        KERNEL_RESIDENT = 0,
         /* one thread runs one track to completion */
         KERNEL_MONOLITHIC = 1,
-        /* the wavefront kernel, general instantiation only */
-        KERNEL_WAVEFRONT_GENERAL = 2
+        /* the resident kernel, general instantiation only */
+        KERNEL_RESIDENT_GENERAL = 2
 };
 
 /* Size of the device scratch buffer launch_transport needs (work cursor and
- * the parked tracks of the wavefront kernel). */
+ * the global work cursor). */
 cudaError_t transport_workspace_bytes(size_t * bytes);
 
 /* Transport n tracks. All pointers are device pointers; `status` receives the

@@ -1,10 +1,10 @@
 /*
- * kernels_spec1.cu -- wavefront kernel specialised at compile time for
+ * kernels_spec1.cu -- resident kernel specialised at compile time for
  * (STRAGGLED, MIXED, BACKWARD, WEIGHTED) in a single infinite medium without
  * locals (examples/pumas/straight.c geometry). Same source as the general
- * kernel (wavefront.cuh); only unreachable code is removed.
+ * kernel (resident.cuh); only unreachable code is removed.
  */
-#include "wavefront.cuh"
+#include "resident.cuh"
 
 namespace pb {
 

@@ -434,13 +434,25 @@ PB_FN void transport_do_ehs(const Physics & p, const Cfg & cfg, Rng & rng,
         step_rotate_direction(rng, state, mu);
 }
 
+/* Alignment points of the step. A GPU scheduler that runs many warps through
+ * step_transport together may re-align them at the `sync.point(k)` marks
+ * (resident.cuh): the step is larger than the instruction cache, and warps that
+ * stay close to each other share the fetched lines. No effect on results; the
+ * default does nothing. The marks sit where every thread of a step passes
+ * exactly once (no early return before the last one in a uniform medium). */
+constexpr int N_SYNC_POINTS = 5;
+struct NoSync {
+        PB_FN void point(int) const {}
+};
+
 /* One Monte Carlo step in a single medium. pumas.c:6296-6925. Returns false
  * on error (trk.error set). */
-template <class Cfg, class Geo, class Rng>
+template <class Cfg, class Geo, class Rng, class Sync = NoSync>
 PB_FN bool step_transport(const Physics & p, const Cfg & cfg,
     const Geo & geo, Track & trk, Rng & rng, State & state, int straight,
     int medium, Locals & locals, double grammage_max, double step_max_medium,
-    int step_max_type, double * step_max_locals, int * out_medium)
+    int step_max_type, double * step_max_locals, int * out_medium,
+    const Sync & sync = Sync())
 {
         trk.n_steps++;
         const int scheme = cfg.energy_loss;
@@ -623,6 +635,7 @@ PB_FN bool step_transport(const Physics & p, const Cfg & cfg,
                 position[2] = end_position[2];
         }
 
+        sync.point(0);
         /* End step kinetic energy. */
         double k1 = state.energy, dk = 0.;
         const double dX = 0.5 * step * (density + locals.density);
@@ -696,6 +709,7 @@ PB_FN bool step_transport(const Physics & p, const Cfg & cfg,
                         }
                 }
 
+                sync.point(1);
                 /* Discrete events by thinning. */
                 double Xmax = dX;
                 if (grammage_max > 0.) {
@@ -770,6 +784,8 @@ PB_FN bool step_transport(const Physics & p, const Cfg & cfg,
                 }
         }
 
+        if (scheme != MODE_STRAGGLED) sync.point(1);
+        sync.point(2);
         /* Grammage. */
         const double Xi = state.grammage;
         state.grammage += dX;
@@ -908,6 +924,7 @@ PB_FN bool step_transport(const Physics & p, const Cfg & cfg,
         state.energy = k1;
         state.distance += step;
 
+        sync.point(3);
         /* End of step multiple scattering path length. */
         if (cfg.scattering == MODE_MIXED) {
                 double mu0, invlb1_;
@@ -995,6 +1012,7 @@ PB_FN bool step_transport(const Physics & p, const Cfg & cfg,
                 for (i = 0; i < 3; i++) direction[i] *= norm;
         }
 
+        sync.point(4);
         /* Soft multiple scattering. */
         if ((invlb1 > 0.) || (trk.step_invlb1 > 0.)) {
                 double ilb1 = 0.25 * step * (invlb1 + trk.step_invlb1);
@@ -1163,9 +1181,10 @@ PB_FN int stepping_rearm(const Physics & p, const Cfg & cfg,
 
 /* One iteration of the stepping loop, pumas.c:5277-5335 and, for a change of
  * medium, 5417-5467 + re-arm. */
-template <class Cfg, class Geo, class Rng>
+template <class Cfg, class Geo, class Rng, class Sync = NoSync>
 PB_FN int stepping_step(const Physics & p, const Cfg & cfg,
-    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp,
+    const Sync & sync = Sync())
 {
         if (!lp.first) {
                 lp.step_max_type = medium_locate(geo, cfg.direction, state,
@@ -1178,7 +1197,7 @@ PB_FN int stepping_step(const Physics & p, const Cfg & cfg,
         int new_medium = -1;
         if (!step_transport(p, cfg, geo, trk, rng, state, lp.straight,
                 lp.medium, lp.locals, lp.grammage_max, lp.step_max_medium,
-                lp.step_max_type, &lp.step_max_locals, &new_medium))
+                lp.step_max_type, &lp.step_max_locals, &new_medium, sync))
                 return PHASE_DONE; /* error: no final protection (:5293) */
         lp.first = 0;
 

