@@ -345,8 +345,9 @@ PB_FN Loc locate_near(
         return locate_near_n(table, p.n_energies, x, hint);
 }
 
-/* table_interpolate_pchip (pumas.c:4146-4157) from a located value. */
-PB_NOINLINE double pchip_at_n(
+/* table_interpolate_pchip (pumas.c:4146-4157) from a located value. Inline:
+ * 34 instructions, fewer than a call costs in register saves around it. */
+PB_FN double pchip_at_n(
     int i1, double t, double dX, const double * table_Y, const double * table_M)
 {
         const int i2 = i1 + 1;

@@ -78,13 +78,23 @@ constexpr int RS_DEL_WARPS = PB_RS_DEL_WARPS;
 constexpr int RS_STEP_WARPS = RS_WARPS - RS_DEL_WARPS;
 constexpr int RS_THREADS = 32 * RS_WARPS;
 constexpr int RS_ENTRIES = PB_RS_ENTRIES; /* DEL parking entries, power of two */
-constexpr int RS_POOL = PB_RS_EHS_POOL ? 32 : 0; /* pool entries per warp */
+#ifndef PB_RS_POOL_ENTRIES
+#define PB_RS_POOL_ENTRIES 32
+#endif
+/* pool entries per warp (<= 32: entry i is served by lane i) */
+constexpr int RS_POOL = PB_RS_EHS_POOL ? PB_RS_POOL_ENTRIES : 0;
+constexpr unsigned int RS_POOL_MASK =
+    (RS_POOL >= 32) ? 0xffffffffu : ((1u << RS_POOL) - 1u);
+static_assert(RS_POOL <= 32, "one lane per pool entry");
 /* A DEL warp starts a pass once that many events are queued (or it has been
  * idle for a while, or the batch is ending). */
 constexpr int RS_DEL_THRESHOLD = 24;
 /* The pools are served every that many rounds. */
-constexpr int RS_EHS_PERIOD = 4;
-constexpr int RS_RING_WORDS = 16;         /* random words per thread */
+constexpr int RS_EHS_PERIOD = 5;
+#ifndef PB_RS_RING_WORDS
+#define PB_RS_RING_WORDS 16
+#endif
+constexpr int RS_RING_WORDS = PB_RS_RING_WORDS; /* random words per thread */
 constexpr unsigned int RS_FULL = 0xffffffffu;
 constexpr int RS_NONE = 0xffff;
 /* Lane phases: PHASE_STEP, PHASE_EHS, PHASE_DEL, PHASE_DONE (pb_transport.h),
@@ -467,12 +477,12 @@ struct MbarSync {
                 asm volatile("{\n"
                              ".reg .pred P1;\n"
                              "RS_WAIT:\n"
-                             "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+                             "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
                              "@P1 bra RS_DONE;\n"
                              "bra RS_WAIT;\n"
                              "RS_DONE:\n"
                              "}" ::"r"(address),
-                             "r"(parity)
+                             "r"(parity), "r"(0x989680u) /* suspend, not spin */
                              : "memory");
         }
 };
@@ -690,7 +700,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 if ((m_ehs | m_empty) != 0) {
                                         const int n_ready = __popc(ready);
                                         const unsigned int vacant =
-                                            ~(ready | pending);
+                                            ~(ready | pending) & RS_POOL_MASK;
                                         const int n_ehs = __popc(m_ehs);
                                         /* ranks: events first, then empty */
                                         const int r = ehs ?
@@ -715,7 +725,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                         if (e >= 0) {
                                                 if (swap && ehs) {
                                                         const uint32_t drawn =
-                                                            park_swap<32>(s,
+                                                            park_swap<(RS_POOL > 0 ? RS_POOL : 1)>(s,
                                                                 rng.count, pool,
                                                                 e);
                                                         rng.seek(a.offset +
@@ -726,7 +736,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                                         to_pending = 1u << e;
                                                 } else if (swap) {
                                                         const uint32_t drawn =
-                                                            park_load<32>(
+                                                            park_load<(RS_POOL > 0 ? RS_POOL : 1)>(
                                                                 s, pool, e);
                                                         rng.seek(a.offset +
                                                                 (uint64_t)
@@ -735,7 +745,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                                         phase = PHASE_STEP;
                                                         to_vacant = 1u << e;
                                                 } else {
-                                                        park_store<32>(
+                                                        park_store<(RS_POOL > 0 ? RS_POOL : 1)>(
                                                             s, rng, pool, e);
                                                         phase = PHASE_EMPTY;
                                                         to_pending = 1u << e;
@@ -897,13 +907,13 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 const bool swap = mine && (phase == PHASE_STEP);
                                 const bool load = mine && (phase == PHASE_EMPTY);
                                 if (swap) {
-                                        const uint32_t drawn = park_swap<32>(
+                                        const uint32_t drawn = park_swap<(RS_POOL > 0 ? RS_POOL : 1)>(
                                             s, rng.count, pool, lane);
                                         rng.seek(a.offset + (uint64_t)s.index,
                                             drawn);
                                 } else if (load) {
                                         const uint32_t drawn =
-                                            park_load<32>(s, pool, lane);
+                                            park_load<(RS_POOL > 0 ? RS_POOL : 1)>(s, pool, lane);
                                         rng.seek(a.offset + (uint64_t)s.index,
                                             drawn);
                                 }
