@@ -923,6 +923,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                     __ballot_sync(RS_FULL, load);
                                 pending &= ~(m_swap | m_load);
                                 ready |= m_swap;
+                                loop_canonical(p, cfg, geo, s.trk, s.lp);
                                 const bool run = swap || load || in_place;
                                 const unsigned int m_run =
                                     __ballot_sync(RS_FULL, run);
@@ -940,6 +941,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
 
                         RS_TICK(RSTAT_T_EHS)
                         /* (d) one Monte Carlo step for every lane */
+                        loop_canonical(p, cfg, geo, s.trk, s.lp);
                         const unsigned int m_step =
                             __ballot_sync(RS_FULL, phase == PHASE_STEP);
                         stat[RSTAT_STEP_LANES] += __popc(m_step);
