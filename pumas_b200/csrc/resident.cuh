@@ -64,7 +64,7 @@ namespace pb {
 #define RS_TICK(k)                                                             \
         {                                                                      \
                 const long long now_ = clock64();                              \
-                stat[k] += (unsigned long long)(now_ - tick);                  \
+                RS_STAT(k, (unsigned long long)(now_ - tick));                 \
                 tick = now_;                                                   \
         }
 #else
@@ -83,6 +83,7 @@ constexpr int RS_ENTRIES = PB_RS_ENTRIES; /* DEL parking entries, power of two *
 #endif
 /* pool entries per warp (<= 32: entry i is served by lane i) */
 constexpr int RS_POOL = PB_RS_EHS_POOL ? PB_RS_POOL_ENTRIES : 0;
+constexpr int RS_POOL_STRIDE = (RS_POOL > 0) ? RS_POOL : 1;
 constexpr unsigned int RS_POOL_MASK =
     (RS_POOL >= 32) ? 0xffffffffu : ((1u << RS_POOL) - 1u);
 static_assert(RS_POOL <= 32, "one lane per pool entry");
@@ -109,22 +110,46 @@ static_assert(RS_STEP_WARPS > 0, "no stepping warp");
 struct RingRng {
         uint32_t key0, key1, trk0, trk1;
         uint32_t count, filled;
-        uint32_t * ring; /* word w of this thread at ring[(w & 15) * RS_THREADS] */
+        uint32_t ring; /* shared memory address: word w of this thread at
+                        * ring + 4 * (w & 15) * RS_THREADS */
+
+        static __device__ __forceinline__ uint32_t lds(uint32_t address)
+        {
+                uint32_t v;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(address));
+                return v;
+        }
+        static __device__ __forceinline__ void sts(uint32_t address, uint32_t v)
+        {
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(address), "r"(v)
+                             : "memory");
+        }
+        __device__ __forceinline__ uint32_t at(uint32_t word) const
+        {
+                return ring +
+                    (word & (RS_RING_WORDS - 1)) * (uint32_t)(4 * RS_THREADS);
+        }
 
         __device__ __forceinline__ void attach(uint32_t * base, uint64_t seed)
         {
-                ring = base;
+                ring = (uint32_t)__cvta_generic_to_shared(base);
                 key0 = (uint32_t)seed;
                 key1 = (uint32_t)(seed >> 32);
                 trk0 = trk1 = count = filled = 0;
         }
 
+        /* The track id of the stream (position in the batch + offset). */
+        __device__ __forceinline__ uint64_t track() const
+        {
+                return (uint64_t)trk0 | ((uint64_t)trk1 << 32);
+        }
+
         __device__ __forceinline__ void put(const uint4 & o)
         {
-                ring[((filled + 0) & (RS_RING_WORDS - 1)) * RS_THREADS] = o.x;
-                ring[((filled + 1) & (RS_RING_WORDS - 1)) * RS_THREADS] = o.y;
-                ring[((filled + 2) & (RS_RING_WORDS - 1)) * RS_THREADS] = o.z;
-                ring[((filled + 3) & (RS_RING_WORDS - 1)) * RS_THREADS] = o.w;
+                sts(at(filled + 0), o.x);
+                sts(at(filled + 1), o.y);
+                sts(at(filled + 2), o.z);
+                sts(at(filled + 3), o.w);
                 filled += 4;
         }
 
@@ -154,8 +179,7 @@ struct RingRng {
         {
                 if ((int)(filled - count) <= 0)
                         put(philox_block(key0, key1, filled >> 2, trk0, trk1));
-                const uint32_t w =
-                    ring[(count & (RS_RING_WORDS - 1)) * RS_THREADS];
+                const uint32_t w = lds(at(count));
                 count++;
                 return ((double)w + 0.5) * (1.0 / 4294967296.0);
         }
@@ -166,7 +190,6 @@ struct Resident {
         State state;
         Track trk;
         Loop lp;
-        long index;  /* position in the batch */
         int medium0; /* first medium (media[0] of the reference) */
 };
 
@@ -194,7 +217,7 @@ constexpr int RS_PARK_WORDS = 31;
 
 template <int STRIDE>
 __device__ __forceinline__ void park_store(const Resident & s,
-    const RingRng & rng, unsigned long long * words, int e)
+    const RingRng & rng, uint64_t offset, unsigned long long * words, int e)
 {
         const State & st = s.state;
         PARK_ST(0, pack_d(st.charge));
@@ -243,14 +266,14 @@ __device__ __forceinline__ void park_store(const Resident & s,
             ((uint32_t)(t.error & 0x1f) << 27);
         PARK_ST(28, pack_2(f0, f1));
         PARK_ST(29, pack_2(t.n_steps, rng.count));
-        PARK_ST(30, (unsigned long long)s.index |
+        PARK_ST(30, (unsigned long long)(rng.track() - offset) |
             ((unsigned long long)(t.iK & 0xff) << 56));
 }
 
-/* Returns the number of variates the track has drawn. */
+/* Loads a parked track and positions the random stream on it. */
 template <int STRIDE>
-__device__ __forceinline__ uint32_t park_load(
-    Resident & s, const unsigned long long * words, int e)
+__device__ __forceinline__ void park_load(Resident & s, RingRng & rng,
+    uint64_t offset, const unsigned long long * words, int e)
 {
         State & st = s.state;
         st.charge = unpack_d(PARK_W(0));
@@ -301,26 +324,21 @@ __device__ __forceinline__ uint32_t park_load(
         const unsigned long long c = PARK_W(29);
         t.n_steps = (uint32_t)c;
         const unsigned long long ix = PARK_W(30);
-        s.index = (long)(ix & 0x00ffffffffffffffull);
         t.iK = (int)(ix >> 56);
-        return (uint32_t)(c >> 32);
+        rng.seek(offset + (ix & 0x00ffffffffffffffull), (uint32_t)(c >> 32));
 }
 
 /* Exchange the track of a lane with a parked one in place (the lane has a
- * pending event and takes over a track whose event has been served). Returns
- * the number of variates the incoming track has drawn; `drawn` is that of the
- * outgoing one. */
+ * pending event and takes over a track whose event has been served). */
 template <int STRIDE>
-__device__ __forceinline__ uint32_t park_swap(Resident & s, uint32_t drawn,
-    unsigned long long * words, int e)
+__device__ __forceinline__ void park_swap(Resident & s, RingRng & rng,
+    uint64_t offset, unsigned long long * words, int e)
 {
         /* the incoming track: all loads in flight together */
         unsigned long long in[RS_PARK_WORDS];
 #pragma unroll
         for (int k = 0; k < RS_PARK_WORDS; k++) in[k] = PARK_W(k);
-        RingRng out_rng;
-        out_rng.count = drawn;
-        park_store<STRIDE>(s, out_rng, words, e);
+        park_store<STRIDE>(s, rng, offset, words, e);
 
         State & st = s.state;
         Track & t = s.trk;
@@ -369,9 +387,8 @@ __device__ __forceinline__ uint32_t park_swap(Resident & s, uint32_t drawn,
         l.first = (int)((g1 >> 26) & 1);
         t.error = (int)((g1 >> 27) & 0x1f);
         t.n_steps = (uint32_t)c;
-        s.index = (long)(ix & 0x00ffffffffffffffull);
         t.iK = (int)(ix >> 56);
-        return (uint32_t)(c >> 32);
+        rng.seek(offset + (ix & 0x00ffffffffffffffull), (uint32_t)(c >> 32));
 }
 #undef PARK_W
 #undef PARK_ST
@@ -435,9 +452,10 @@ __device__ __forceinline__ int ring_pop_warp(
 
 /* Write a finished track back to HBM. */
 __device__ __forceinline__ void resident_flush(const Resident & s,
-    uint32_t drawn, const Outcome & out, const BatchArgs & a)
+    const RingRng & rng, const Outcome & out, const BatchArgs & a)
 {
-        const long i = s.index;
+        const long i = (long)(rng.track() - a.offset);
+        const uint32_t drawn = rng.count;
         a.states[i] = s.state;
         if (a.events != nullptr) a.events[i] = out.event;
         if (a.media != nullptr) {
@@ -510,27 +528,6 @@ struct ResidentShared {
 constexpr size_t RS_POOL_BYTES =
     (size_t)RS_PARK_WORDS * RS_POOL * sizeof(unsigned long long);
 
-/* Shared memory of one CTA: control block, queues, random number rings, the
- * DEL parking area and, when the configuration has hard elastic events
- * (mixed scattering), the warp pools. What is left of the SM's 256 KB is L1
- * for the physics tables and the register spills. */
-constexpr size_t RS_PARK_BYTES =
-    (size_t)RS_PARK_WORDS * RS_ENTRIES * sizeof(unsigned long long);
-
-__host__ __device__ constexpr size_t resident_smem_bytes(bool pooled)
-{
-        return ((sizeof(ResidentShared) + 15) & ~(size_t)15) +
-            3 * RS_ENTRIES * sizeof(unsigned short) +
-            (size_t)RS_RING_WORDS * RS_THREADS * sizeof(uint32_t) +
-            RS_PARK_BYTES + (pooled ? RS_POOL_BYTES * RS_STEP_WARPS : 0);
-}
-
-/* Do hard elastic events go through the warp pools? */
-template <class Cfg> __host__ __device__ inline bool resident_pooled(const Cfg & cfg)
-{
-        return (RS_POOL > 0) && (cfg.scattering == MODE_MIXED);
-}
-
 /* Scheduler statistics (diagnostics), summed over warps. */
 enum {
         RSTAT_ROUNDS = 0,
@@ -549,6 +546,29 @@ enum {
         N_RSTATS
 };
 static_assert(N_RSTATS <= N_STATS, "statistics buffer");
+
+/* Shared memory of one CTA: control block, queues, random number rings, the
+ * DEL parking area and, when the configuration has hard elastic events
+ * (mixed scattering), the warp pools. What is left of the SM's 256 KB is L1
+ * for the physics tables and the register spills. */
+constexpr size_t RS_PARK_BYTES =
+    (size_t)RS_PARK_WORDS * RS_ENTRIES * sizeof(unsigned long long);
+
+__host__ __device__ constexpr size_t resident_smem_bytes(bool pooled)
+{
+        return ((sizeof(ResidentShared) + 15) & ~(size_t)15) +
+            3 * RS_ENTRIES * sizeof(unsigned short) +
+            (size_t)RS_RING_WORDS * RS_THREADS * sizeof(uint32_t) +
+            (size_t)RS_WARPS * N_RSTATS * sizeof(unsigned long long) +
+            RS_PARK_BYTES + (pooled ? RS_POOL_BYTES * RS_STEP_WARPS : 0);
+}
+
+/* Do hard elastic events go through the warp pools? */
+template <class Cfg> __host__ __device__ inline bool resident_pooled(const Cfg & cfg)
+{
+        return (RS_POOL > 0) && (cfg.scattering == MODE_MIXED);
+}
+
 
 template <class Cfg, class Geo>
 __global__ void __launch_bounds__(RS_THREADS, 1)
@@ -569,6 +589,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
         at += 3 * RS_ENTRIES * sizeof(unsigned short);
         uint32_t * const rings = reinterpret_cast<uint32_t *>(at);
         at += (size_t)RS_RING_WORDS * RS_THREADS * sizeof(uint32_t);
+        unsigned long long * const stats =
+            reinterpret_cast<unsigned long long *>(at);
+        at += (size_t)RS_WARPS * N_RSTATS * sizeof(unsigned long long);
         unsigned long long * const park =
             reinterpret_cast<unsigned long long *>(at);
         at += RS_PARK_BYTES;
@@ -600,9 +623,16 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
         }
         __syncthreads();
 
-        unsigned long long stat[N_RSTATS];
-#pragma unroll
-        for (int k = 0; k < N_RSTATS; k++) stat[k] = 0;
+        /* scheduler statistics: per warp counters in shared memory (in
+         * registers they would cost every thread 26 of its 128) */
+        unsigned long long * const wstat = stats + warp * N_RSTATS;
+        if (lane < N_RSTATS) wstat[lane] = 0;
+        __syncwarp();
+#define RS_STAT(k, v)                                                          \
+        {                                                                      \
+                const unsigned long long v_ = (v); /* (by all lanes) */        \
+                if (lane == 0) wstat[k] += v_;                                 \
+        }
 
         Resident s;
         RingRng rng;
@@ -624,10 +654,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 int flushed = 0;
                                 if (e >= 0) {
                                         RS_FENCE();
-                                        const uint32_t drawn =
-                                            park_load<RS_ENTRIES>(s, park, e);
-                                        rng.seek(a.offset + (uint64_t)s.index,
-                                            drawn);
+                                        park_load<RS_ENTRIES>(
+                                            s, rng, a.offset, park, e);
                                         rng.top_up();
                                         const int ph = stepping_del(p, cfg, geo,
                                             s.trk, rng, s.state, s.lp);
@@ -638,13 +666,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                                     -1 :
                                                     s.medium0;
                                                 track_end(s.trk, s.lp, out);
-                                                resident_flush(
-                                                    s, rng.count, out, a);
+                                                resident_flush(s, rng, out, a);
                                                 ring_push(free_q, &sh.free_, e);
                                                 flushed = 1;
                                         } else {
                                                 park_store<RS_ENTRIES>(
-                                                    s, rng, park, e);
+                                                    s, rng, a.offset, park, e);
                                                 RS_FENCE();
                                                 ring_push(ret_q, &sh.ret_, e);
                                         }
@@ -657,8 +684,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                         __threadfence();
                                         atomicSub(&sh.live, __popc(fl));
                                 }
-                                stat[RSTAT_DEL_PASSES]++;
-                                stat[RSTAT_DEL_LANES] += __popc(got);
+                                RS_STAT(RSTAT_DEL_PASSES, 1)
+                                RS_STAT(RSTAT_DEL_LANES, __popc(got))
                                 idle = 0;
                         } else if (over) {
                                 break;
@@ -724,35 +751,31 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                         unsigned int to_vacant = 0;
                                         if (e >= 0) {
                                                 if (swap && ehs) {
-                                                        const uint32_t drawn =
-                                                            park_swap<(RS_POOL > 0 ? RS_POOL : 1)>(s,
-                                                                rng.count, pool,
-                                                                e);
-                                                        rng.seek(a.offset +
-                                                                (uint64_t)
-                                                                    s.index,
-                                                            drawn);
+                                                        park_swap<
+                                                            RS_POOL_STRIDE>(s,
+                                                            rng, a.offset,
+                                                            pool, e);
                                                         phase = PHASE_STEP;
                                                         to_pending = 1u << e;
                                                 } else if (swap) {
-                                                        const uint32_t drawn =
-                                                            park_load<(RS_POOL > 0 ? RS_POOL : 1)>(
-                                                                s, pool, e);
-                                                        rng.seek(a.offset +
-                                                                (uint64_t)
-                                                                    s.index,
-                                                            drawn);
+                                                        park_load<
+                                                            RS_POOL_STRIDE>(s,
+                                                            rng, a.offset,
+                                                            pool, e);
                                                         phase = PHASE_STEP;
                                                         to_vacant = 1u << e;
                                                 } else {
-                                                        park_store<(RS_POOL > 0 ? RS_POOL : 1)>(
-                                                            s, rng, pool, e);
+                                                        park_store<
+                                                            RS_POOL_STRIDE>(s,
+                                                            rng, a.offset,
+                                                            pool, e);
                                                         phase = PHASE_EMPTY;
                                                         to_pending = 1u << e;
                                                 }
-                                        } else if (ehs) {
-                                                stat[RSTAT_WAITS]++;
                                         }
+                                        RS_STAT(RSTAT_WAITS,
+                                            __popc(__ballot_sync(RS_FULL,
+                                                ehs && (e < 0))))
                                         to_pending = __reduce_or_sync(
                                             RS_FULL, to_pending);
                                         to_vacant = __reduce_or_sync(
@@ -768,7 +791,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                          * lanes */
                         if (__any_sync(RS_FULL, (phase != PHASE_STEP) &&
                                 (!pooled || (phase != PHASE_EHS)))) {
-                                stat[RSTAT_SERVICES]++;
+                                RS_STAT(RSTAT_SERVICES, 1)
                                 /* finished tracks go back to HBM */
                                 const bool done = (phase == PHASE_DONE);
                                 if (done) {
@@ -777,7 +800,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                             -1 :
                                             s.medium0;
                                         track_end(s.trk, s.lp, out);
-                                        resident_flush(s, rng.count, out, a);
+                                        resident_flush(s, rng, out, a);
                                         phase = PHASE_EMPTY;
                                 }
                                 int gone = __popc(__ballot_sync(RS_FULL, done));
@@ -790,38 +813,35 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 int e = ring_pop_warp(ret_q, &sh.ret_, del, lane);
                                 if (e >= 0) {
                                         RS_FENCE();
-                                        const uint32_t drawn =
-                                            park_swap<RS_ENTRIES>(
-                                                s, rng.count, park, e);
+                                        park_swap<RS_ENTRIES>(
+                                            s, rng, a.offset, park, e);
                                         RS_FENCE();
                                         ring_push(del_q, &sh.del_, e);
-                                        rng.seek(a.offset + (uint64_t)s.index,
-                                            drawn);
                                         phase = PHASE_STEP;
                                 }
                                 const bool del_2 = (phase == PHASE_DEL);
                                 e = ring_pop_warp(
                                     free_q, &sh.free_, del_2, lane);
                                 if (e >= 0) {
-                                        park_store<RS_ENTRIES>(s, rng, park, e);
+                                        park_store<RS_ENTRIES>(
+                                            s, rng, a.offset, park, e);
                                         RS_FENCE();
                                         ring_push(del_q, &sh.del_, e);
                                         phase = PHASE_EMPTY;
-                                } else if (del_2) {
-                                        stat[RSTAT_WAITS]++;
                                 }
+                                RS_STAT(RSTAT_WAITS,
+                                    __popc(__ballot_sync(
+                                        RS_FULL, del_2 && (e < 0))))
 
                                 /* take back tracks whose event was served */
                                 e = ring_pop_warp(ret_q, &sh.ret_,
                                     phase == PHASE_EMPTY, lane);
                                 if (e >= 0) {
                                         RS_FENCE();
-                                        const uint32_t drawn =
-                                            park_load<RS_ENTRIES>(s, park, e);
+                                        park_load<RS_ENTRIES>(
+                                            s, rng, a.offset, park, e);
                                         RS_FENCE();
                                         ring_push(free_q, &sh.free_, e);
-                                        rng.seek(a.offset + (uint64_t)s.index,
-                                            drawn);
                                         phase = PHASE_STEP;
                                 }
 
@@ -852,7 +872,6 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                         if ((phase == PHASE_EMPTY) &&
                                             (rank < got)) {
                                                 const long i = base + rank;
-                                                s.index = i;
                                                 s.state = a.states[i];
                                                 rng.seek(
                                                     a.offset + (uint64_t)i, 0);
@@ -862,8 +881,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                                     out);
                                                 s.medium0 = out.medium[0] & 0xff;
                                                 if (phase == PHASE_DONE) {
-                                                        resident_flush(s,
-                                                            rng.count, out, a);
+                                                        resident_flush(s, rng, out, a);
                                                         phase = PHASE_EMPTY;
                                                         early = true;
                                                 }
@@ -893,7 +911,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                         if (__all_sync(RS_FULL, phase != PHASE_STEP))
                                 __nanosleep(200);
 #endif
-                        stat[RSTAT_ROUNDS]++;
+                        RS_STAT(RSTAT_ROUNDS, 1)
                         RS_TICK(RSTAT_T_BARRIER)
 
                         /* (c) every `period` rounds, all warps together: the
@@ -906,17 +924,12 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 const bool in_place = (phase == PHASE_EHS);
                                 const bool swap = mine && (phase == PHASE_STEP);
                                 const bool load = mine && (phase == PHASE_EMPTY);
-                                if (swap) {
-                                        const uint32_t drawn = park_swap<(RS_POOL > 0 ? RS_POOL : 1)>(
-                                            s, rng.count, pool, lane);
-                                        rng.seek(a.offset + (uint64_t)s.index,
-                                            drawn);
-                                } else if (load) {
-                                        const uint32_t drawn =
-                                            park_load<(RS_POOL > 0 ? RS_POOL : 1)>(s, pool, lane);
-                                        rng.seek(a.offset + (uint64_t)s.index,
-                                            drawn);
-                                }
+                                if (swap)
+                                        park_swap<RS_POOL_STRIDE>(
+                                            s, rng, a.offset, pool, lane);
+                                else if (load)
+                                        park_load<RS_POOL_STRIDE>(
+                                            s, rng, a.offset, pool, lane);
                                 const unsigned int m_swap =
                                     __ballot_sync(RS_FULL, swap);
                                 const unsigned int m_load =
@@ -928,8 +941,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 const unsigned int m_run =
                                     __ballot_sync(RS_FULL, run);
                                 if (m_run != 0) {
-                                        stat[RSTAT_EHS_PASSES]++;
-                                        stat[RSTAT_EHS_LANES] += __popc(m_run);
+                                        RS_STAT(RSTAT_EHS_PASSES, 1)
+                                        RS_STAT(RSTAT_EHS_LANES, __popc(m_run))
                                 }
                                 if (run) {
                                         rng.top_up();
@@ -944,7 +957,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                         loop_canonical(p, cfg, geo, s.trk, s.lp);
                         const unsigned int m_step =
                             __ballot_sync(RS_FULL, phase == PHASE_STEP);
-                        stat[RSTAT_STEP_LANES] += __popc(m_step);
+                        RS_STAT(RSTAT_STEP_LANES, __popc(m_step))
                         if (StepSync<Cfg, Geo>::enabled) {
                                 MbarSync sync;
                                 sync.base = (uint32_t)__cvta_generic_to_shared(
@@ -986,7 +999,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
         if ((a.stats != nullptr) && (lane == 0)) {
 #pragma unroll
                 for (int k = 0; k < N_RSTATS; k++)
-                        atomicAdd(a.stats + k, stat[k]);
+                        atomicAdd(a.stats + k, wstat[k]);
         }
 }
 
