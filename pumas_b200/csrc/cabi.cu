@@ -264,6 +264,8 @@ const char * return_text(int rc)
                 return "bad norm for state direction";
         case PUMAS_RETURN_MISSING_LIMIT:
                 return "infinite medium without external limit(s)";
+        case PUMAS_RETURN_VALUE_ERROR: /* pumas.c:5133 */
+                return "magnetic rotation is too strong";
         default:
                 return "transport error";
         }

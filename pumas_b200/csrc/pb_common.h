@@ -122,6 +122,7 @@ constexpr int STEP_RAW = 1;
 /* enum pumas_return codes raised from inside the transport (pumas.h:143) */
 constexpr int RETURN_SUCCESS = 0;
 constexpr int RETURN_DENSITY_ERROR = 4;
+constexpr int RETURN_VALUE_ERROR = 24;
 
 /* Binary layout of struct pumas_state (pumas.h:289-309). */
 struct State {

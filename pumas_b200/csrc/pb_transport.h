@@ -12,9 +12,7 @@
  *   step_rotate_direction        src/pumas.c:7042-7095   [a10]
  * The hidden per-context stepping state of the reference
  * (struct simulation_context, pumas.c:426-477) lives in `Track`, private to the
- * thread; the recorder hooks are out of scope and the
- * magnetised closed-form CSDA (transport_csda_deflect, pumas.c:4968) falls
- * back to stepping.
+ * thread; the recorder hooks are out of scope.
  *
  * The number and order of the uniform variates drawn from `Rng` is part of the
  * contract with the oracle.
@@ -1318,11 +1316,167 @@ PB_FN int stepping_ehs(const Physics & p, const Cfg & cfg,
         return stepping_rearm(p, cfg, geo, trk, rng, state, lp, true);
 }
 
-/* Closed form CSDA in a uniform, field free medium. pumas.c:4777-4949. */
+/* Total magnetic transport within the CSDA, uniform medium: the Larmor
+ * polynomials of the phase on the tabulated moments Li. pumas.c:5095-5168.
+ * Returns false when the rotation exceeds the range of the polynomials
+ * (PUMAS_RETURN_VALUE_ERROR, pumas.c:5133-5136). */
+PB_NOINLINE bool csda_magnetic_transport(const Physics & p, int material,
+    double density, double magnet, double charge, double kinetic, double phase,
+    double * x, double * y, double * z)
+{
+        const int imax = p.n_energies - 1;
+        double k0 = kinetic;
+        int i1, i2;
+        if (kinetic <= p.K[0]) {
+                k0 = p.K[0];
+                i1 = 0;
+                i2 = 1;
+        } else if (kinetic >= p.K[imax]) {
+                /* deflection neglected at very high energy */
+                *y = 0.0;
+                *x = *z = -(cel_grammage(p, MODE_CSDA, material, kinetic) -
+                    col_sm(p, p.X, MODE_CSDA, material)[imax]);
+                return true;
+        } else {
+                i1 = table_index(p, p.K, k0);
+                i2 = i1 + 1;
+        }
+
+        const double max_phi = 2.0 * PI;
+        const double poly_x[N_LARMOR_ORDERS] = { 1.000000000e+000,
+                0.000000000e+000, -5.000000000e-001, -1.048969541e-002,
+                5.597396438e-002, -6.401353612e-003, -4.495849930e-004,
+                6.583532135e-005 };
+        const double poly_y[N_LARMOR_ORDERS] = { 0.000000000e+000,
+                1.000000000e+000, -1.400755143e-002, -1.350173383e-001,
+                -2.838778336e-002, 2.123237056e-002, -3.094290091e-003,
+                1.409012754e-004 };
+        if (fabs(phase) > max_phi) return false;
+
+        /* table_get_Li, pumas.c:4594-4599 */
+        const double * const Li =
+            p.Li + (size_t)material * N_LARMOR_ORDERS * p.n_energies;
+        double x1, x2, y1, y2, z1, z2;
+        {
+                const double a = -magnet * charge / density;
+                x1 = x2 = y1 = y2 = 0.;
+                double u = 1.;
+                for (int j = 0; j < N_LARMOR_ORDERS; j++) {
+                        const double l1 = Li[j * p.n_energies + i1];
+                        const double l2 = Li[j * p.n_energies + i2];
+                        x1 += u * poly_x[j] * l1;
+                        y1 += u * poly_y[j] * l1;
+                        x2 += u * poly_x[j] * l2;
+                        y2 += u * poly_y[j] * l2;
+                        u *= a;
+                }
+                z1 = Li[i1];
+                z2 = Li[i2];
+        }
+        {
+                const double h = (k0 - p.K[i1]) / (p.K[i2] - p.K[i1]);
+                *x = (x1 + h * (x2 - x1)) / density;
+                *y = (y1 + h * (y2 - y1)) / density;
+                *z = (z1 + h * (z2 - z1)) / density;
+        }
+        return true;
+}
+
+/* Magnetic deflection of the closed form CSDA in a uniform field.
+ * pumas.c:4968-5075. `state.energy` is the final kinetic energy. Returns a
+ * pumas_return code. */
+PB_NOINLINE int transport_csda_deflect(const Physics & p, int direction_mode,
+    State & state, int material, const Locals & locals, double ki,
+    double distance)
+{
+        (void)direction_mode;
+        const double charge = state.charge;
+        const double kf = state.energy;
+        double * const position = state.position;
+        double * const direction = state.direction;
+        const double density = locals.density;
+        const double * const magnet = locals.magnet;
+
+        double b0, ex[3], ey[3], ez[3];
+        {
+                b0 = sqrt(magnet[0] * magnet[0] + magnet[1] * magnet[1] +
+                    magnet[2] * magnet[2]);
+                const double b0_i = 1.0 / b0;
+                ey[0] = (direction[2] * magnet[1] - direction[1] * magnet[2]) *
+                    b0_i;
+                ey[1] = (direction[0] * magnet[2] - direction[2] * magnet[0]) *
+                    b0_i;
+                ey[2] = (direction[1] * magnet[0] - direction[0] * magnet[1]) *
+                    b0_i;
+                {
+                        const double d = b0_i * b0_i *
+                            (magnet[0] * direction[0] +
+                                magnet[1] * direction[1] +
+                                magnet[2] * direction[2]);
+                        ez[0] = magnet[0] * d;
+                        ez[1] = magnet[1] * d;
+                        ez[2] = magnet[2] * d;
+                }
+                ex[0] = direction[0] - ez[0];
+                ex[1] = direction[1] - ez[1];
+                ex[2] = direction[2] - ez[2];
+        }
+
+        double dx, dy, dz, dp;
+        {
+                const double a = -b0 * charge / density;
+                const double pi = a * cel_magnetic_rotation(p, material, ki);
+                const double pf = a * cel_magnetic_rotation(p, material, kf);
+                dp = pf - pi;
+
+                const double ps = fabs(pi + pf);
+                if (ps == 0.) return RETURN_SUCCESS;
+                const double dp0 = fabs(dp);
+                if ((dp0 < 1E-02) && (dp0 / ps < 1E-02)) {
+                        if (ki >= kf)
+                                dz = distance;
+                        else
+                                dz = -distance;
+                        const double sixth = 1 / 6.0;
+                        dx = dz * (1.0 - sixth * dp * dp);
+                        dy = 0.5 * dz * dp;
+                } else {
+                        double xi, yi, zi, xf, yf, zf;
+                        if (!csda_magnetic_transport(p, material, density, b0,
+                                charge, ki, pi, &xi, &yi, &zi))
+                                return RETURN_VALUE_ERROR;
+                        if (!csda_magnetic_transport(p, material, density, b0,
+                                charge, kf, pf, &xf, &yf, &zf))
+                                return RETURN_VALUE_ERROR;
+                        {
+                                const double si = xsin(pi);
+                                const double ci = xcos(pi);
+                                xf -= xi;
+                                yf -= yi;
+                                dx = ci * xf + si * yf;
+                                dy = -si * xf + ci * yf;
+                        }
+                        dz = zf - zi;
+                }
+        }
+        position[0] += dx * ex[0] + dy * ey[0] + dz * ez[0];
+        position[1] += dx * ex[1] + dy * ey[1] + dz * ez[1];
+        position[2] += dx * ex[2] + dy * ey[2] + dz * ez[2];
+
+        const double s = xsin(dp);
+        const double c = xcos(dp);
+        direction[0] = c * ex[0] + s * ey[0] + ez[0];
+        direction[1] = c * ex[1] + s * ey[1] + ez[1];
+        direction[2] = c * ex[2] + s * ey[2] + ez[2];
+        return RETURN_SUCCESS;
+}
+
+/* Closed form CSDA in a uniform medium. pumas.c:4777-4949. `*rc` receives the
+ * return code of the magnetic deflection (pumas.c:4929-4933). */
 template <class Cfg, class Geo>
 PB_FN int transport_with_csda(const Physics & p, const Cfg & cfg,
     const Geo & geo, const Track & trk, State & state, int medium,
-    const Locals & locals)
+    const Locals & locals, int * rc)
 {
         const int material = geo_material(geo, medium);
         const double density = locals.density;
@@ -1451,14 +1605,19 @@ PB_FN int transport_with_csda(const Physics & p, const Cfg & cfg,
         if (cfg.decay == MODE_WEIGHTED)
                 state.weight *= xexp(-fabs(ti - state.time) / p.ctau);
 
-        double path;
-        if (cfg.direction == MODE_FORWARD)
-                path = distance;
-        else
-                path = -distance;
-        state.position[0] += path * state.direction[0];
-        state.position[1] += path * state.direction[1];
-        state.position[2] += path * state.direction[2];
+        if (geo_has_locals(geo) && (locals.magnetized != 0)) {
+                *rc = transport_csda_deflect(
+                    p, cfg.direction, state, material, locals, ki, distance);
+        } else {
+                double path;
+                if (cfg.direction == MODE_FORWARD)
+                        path = distance;
+                else
+                        path = -distance;
+                state.position[0] += path * state.direction[0];
+                state.position[1] += path * state.direction[1];
+                state.position[2] += path * state.direction[2];
+        }
 
         return event;
 }
@@ -1562,17 +1721,15 @@ PB_FN int track_begin(const Physics & p, const Cfg & cfg,
                         out.rc = 15; /* PUMAS_RETURN_MISSING_LIMIT */
                         return PHASE_DONE;
                 } else if ((cfg.scattering == MODE_DISABLED) &&
-                    (cfg.energy_loss == MODE_CSDA) && !locals.magnetized) {
-                        /* (magnetised closed form: stepping instead, see the
-                         * header comment) */
+                    (cfg.energy_loss == MODE_CSDA)) {
                         do_stepping = 0;
                 }
         }
 
         lp.medium = medium;
         if (!do_stepping) {
-                out.event =
-                    transport_with_csda(p, cfg, geo, trk, state, medium, locals);
+                out.event = transport_with_csda(
+                    p, cfg, geo, trk, state, medium, locals, &out.rc);
                 out.medium[1] = medium;
                 return PHASE_DONE;
         }

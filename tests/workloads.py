@@ -67,6 +67,31 @@ def csda_water(material, n, seed=0):
         states=make_states(n, 1e3))
 
 
+def csda_magnet(material, n, seed=0, direction=MODE_FORWARD):
+    """Closed form CSDA in a uniform magnetised medium: transport_csda_deflect
+    and csda_magnetic_transport (pumas.c:4968-5168), both the small rotation
+    expansion and the Larmor polynomials, both charges."""
+    geo = uniform_geometry(material("Air"), density=1.205)
+    for k, b in enumerate((0., 2e-5, -4e-5)):
+        geo.layer[0].magnet[k] = b
+    rng = np.random.default_rng(seed)
+    charge = np.where(rng.uniform(size=n) > 0.5, 1., -1.)
+    if direction == MODE_FORWARD:
+        energy = log_uniform(n, 0.05, 1e3, seed + 1)
+        limit = dict(event=EVENT_LIMIT_DISTANCE,
+                     limit_distance=3e3)
+    else:
+        energy = log_uniform(n, 0.05, 1e2, seed + 1)
+        limit = dict(event=EVENT_LIMIT_DISTANCE | EVENT_LIMIT_ENERGY,
+                     limit_distance=3e3, limit_energy=2e2)
+    return dict(
+        settings=make_settings(MODE_CSDA, MODE_DISABLED, direction=direction,
+                               **limit),
+        geometry=geo,
+        states=make_states(n, energy, charge=charge,
+                           direction=isotropic(n, seed + 2)))
+
+
 def csda_spectrum(material, n, seed=0, direction=MODE_FORWARD):
     """Closed form CSDA over 10 decades of energy with every limit armed."""
     return dict(
@@ -233,6 +258,9 @@ WORKLOADS = {
     "csda_spectrum_fwd": ("materials.muon", csda_spectrum, {}),
     "csda_spectrum_bwd": ("materials.muon", csda_spectrum,
                           dict(direction=MODE_BACKWARD)),
+    "csda_magnet_fwd": ("materials.muon", csda_magnet, {}),
+    "csda_magnet_bwd": ("materials.muon", csda_magnet,
+                        dict(direction=MODE_BACKWARD)),
     "rock_3km": ("materials.muon", rock_3km, {}),
     "mixed_loss": ("materials.muon", mixed_loss, {}),
     "mixed_loss_scattering": ("materials.muon", mixed_loss,
