@@ -6,6 +6,10 @@ interchange format between the reference and the GPU library:
 both sides load the same bytes. Outputs (gzip, committed):
     tests/golden/materials.muon.pumas.gz   examples/data/materials.xml, muon
     tests/golden/ice.tau.pumas.gz          oracle/data/ice.xml, tau
+    tests/golden/rock.muon.kkb.pumas.gz    oracle/data/rock.xml, muon, models
+                                           KKP / KKP / BBKS
+    tests/golden/rock.muon.abm.pumas.gz    oracle/data/rock.xml, muon, models
+                                           ABB / SSR / BM
 """
 import ctypes
 import gzip
@@ -17,16 +21,28 @@ lib = ctypes.CDLL(os.path.join(HERE, "_ref", "libpumas_oracle.so"))
 lib.oracle_physics_create_and_dump.argtypes = [
     ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p]
 
-JOBS = [
-    (0, "examples/materials.xml", "materials.muon.pumas"),
-    (1, "ice/ice.xml", "ice.tau.pumas"),
-]
+lib.oracle_physics_create_and_dump_models.argtypes = [
+    ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p,
+    ctypes.c_char_p, ctypes.c_char_p]
 
-for particle, mdf, name in JOBS:
+JOBS = [
+    (0, "examples/materials.xml", "materials.muon.pumas", None),
+    (1, "ice/ice.xml", "ice.tau.pumas", None),
+    (0, "rock/rock.xml", "rock.muon.kkb.pumas", (b"KKP", b"KKP", b"BBKS")),
+    (0, "rock/rock.xml", "rock.muon.abm.pumas", (b"ABB", b"SSR", b"BM")),
+]
+if len(sys.argv) > 1:
+    JOBS = [j for j in JOBS if j[2] in sys.argv[1:]]
+
+for particle, mdf, name, models in JOBS:
     mdf_path = os.path.join(HERE, "_ref", "data", mdf)
     raw = os.path.join(HERE, "_ref", "data", name)
-    rc = lib.oracle_physics_create_and_dump(
-        particle, mdf_path.encode(), None, raw.encode())
+    if models is None:
+        rc = lib.oracle_physics_create_and_dump(
+            particle, mdf_path.encode(), None, raw.encode())
+    else:
+        rc = lib.oracle_physics_create_and_dump_models(
+            particle, mdf_path.encode(), raw.encode(), *models)
     if rc != 0:
         sys.exit(f"pumas_physics_create failed for {mdf} (rc={rc})")
     out = os.path.join(HERE, "..", "tests", "golden", name + ".gz")

@@ -298,6 +298,31 @@ int oracle_physics_create_and_dump(int particle, const char * mdf_path,
         return rc;
 }
 
+/* Same, with the DCS models named (NULL = default). pumas.h:742-772. */
+int oracle_physics_create_and_dump_models(int particle, const char * mdf_path,
+    const char * dump_path, const char * bremsstrahlung,
+    const char * pair_production, const char * photonuclear)
+{
+        struct pumas_physics_settings settings;
+        memset(&settings, 0x0, sizeof settings);
+        settings.bremsstrahlung = bremsstrahlung;
+        settings.pair_production = pair_production;
+        settings.photonuclear = photonuclear;
+        struct pumas_physics * physics = NULL;
+        int rc = pumas_physics_create(&physics, (enum pumas_particle)particle,
+            mdf_path, NULL, &settings);
+        if (rc != PUMAS_RETURN_SUCCESS) return rc;
+        FILE * stream = fopen(dump_path, "wb");
+        if (stream == NULL) {
+                pumas_physics_destroy(&physics);
+                return PUMAS_RETURN_PATH_ERROR;
+        }
+        rc = pumas_physics_dump(physics, stream);
+        fclose(stream);
+        pumas_physics_destroy(&physics);
+        return rc;
+}
+
 /* Raw table access for loader parity tests: returns the address and length
  * (in doubles) of the named table of the reference's physics object. */
 const double * oracle_table(

@@ -1,8 +1,9 @@
 /*
  * pb_dcs.h -- differential cross-sections (DCS) of the discrete energy losses.
  *
- * Restates, for the DEFAULT models only (SSR bremsstrahlung, SSR pair
- * production, DRSS photonuclear; src/pumas.c:192-200):
+ * Restates, for the default models (SSR bremsstrahlung, SSR pair production,
+ * DRSS photonuclear; src/pumas.c:192-200; the other models of the reference
+ * are in pb_dcs_models.h):
  *   - dcs_evaluate, the single precision log-log PCHIP over table_DCS with its
  *     fall back to the exact model (pumas.c:11243-11347)           [a16]
  *   - the ionisation DCS and its sampler (pumas.c:11082-11226)      [a17]
@@ -742,6 +743,21 @@ PB_NOINLINE double dcs_photonuclear_DRSS(
         return (ds < 0.) ? 0. : ds;
 }
 
+} /* namespace pb */
+#include "pb_dcs_models.h"
+namespace pb {
+
+/* The doubly differential photonuclear cross-section of the physics
+ * (dcs_photonuclear_ddcs, pumas.c:15160-15170): BM has its own, DRSS and
+ * BBKS share the DRSS one. */
+PB_FN double dcs_photonuclear_d2(const Physics & p, const Element & el,
+    double ml, double K, double q, double Q2)
+{
+        if (p.model[2] == PHOTONUCLEAR_BM)
+                return dcs_photonuclear_d2_BM(el, ml, K, q, Q2);
+        return dcs_photonuclear_d2_DRSS(el, ml, K, q, Q2);
+}
+
 /* ---- process dispatch (dcs_get, pumas.c:10954; wrappers 11003-11048) ----- */
 PB_FN double dcs_model(
     const Physics & p, int process, const Element & el, double K, double q)
@@ -749,14 +765,27 @@ PB_FN double dcs_model(
         if (process == 3) return dcs_ionisation(p, el, K, q);
         double d;
         if (process == 0) {
-                d = dcs_bremsstrahlung_SSR(p, el, p.mass, K, q);
+                if (p.model[0] == BREMSSTRAHLUNG_KKP)
+                        d = dcs_bremsstrahlung_KKP(el, p.mass, K, q);
+                else if (p.model[0] == BREMSSTRAHLUNG_ABB)
+                        d = dcs_bremsstrahlung_ABB(el, p.mass, K, q);
+                else
+                        d = dcs_bremsstrahlung_SSR(p, el, p.mass, K, q);
         } else if (process == 1) {
-                d = dcs_pair_production_SSR(p, el, p.mass, K, q);
+                if (p.model[1] == PAIR_PRODUCTION_KKP)
+                        d = dcs_pair_production_KKP(el, p.mass, K, q);
+                else
+                        d = dcs_pair_production_SSR(p, el, p.mass, K, q);
         } else {
                 double qmin, qmax;
                 dcs_photonuclear_range(p.mass, K, &qmin, &qmax);
                 if ((q < qmin) || (q > qmax)) return 0.;
-                d = dcs_photonuclear_DRSS(el, p.mass, K, q);
+                if (p.model[2] == PHOTONUCLEAR_BM)
+                        d = dcs_photonuclear_BM(el, p.mass, K, q);
+                else if (p.model[2] == PHOTONUCLEAR_BBKS)
+                        d = dcs_photonuclear_BBKS(el, p.mass, K, q);
+                else
+                        d = dcs_photonuclear_DRSS(el, p.mass, K, q);
         }
         return d * 1E+03 * AVOGADRO_NUMBER * (p.mass + K) / el.A;
 }

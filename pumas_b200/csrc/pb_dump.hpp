@@ -106,6 +106,7 @@ struct HostPhysics {
         std::vector<std::string> element_name;
         std::vector<double> material_I;
         std::string model[3];
+        int model_index[3];
         int n_energy_loss_header;
 
         /* Instantiate the view over a copy of `image` located at `base`. */
@@ -186,6 +187,21 @@ inline void element_fill(Element & e, double Z, double A, double I)
         e.z23 = pow(Z, twothird);
         e.Dn = 1.54 * pow(A, e027);
         e.lnA = log(A);
+        e.a13 = pow(A, third);
+        if (Z == 1) {
+                e.wood_saxon = 0.;
+        } else {
+                /* dcs_wood_saxon, pumas.c:14732-14748 */
+                volatile double two = 2.;
+                double r0 = e.a13;
+                r0 = 1.12 * r0 - 0.86 / r0;
+                const double a = 0.54;
+                const double zeta3 = 1.202056903159594;
+                const double V = a *
+                    (r0 * r0 * log(two) + a * r0 * M_PI * M_PI / 6. +
+                        a * a * 1.5 * zeta3);
+                e.wood_saxon = 1. - 4. * M_PI * 0.17 * V / A;
+        }
 }
 
 } /* namespace detail */
@@ -241,10 +257,13 @@ inline int load_physics_bytes(
                 return 11;
         }
 
-        /* Model names: only the defaults have device implementations. */
+        /* Model names -> indices (pb_dcs_models.h; dcs_stack,
+         * pumas.c:15381-15390). User registered models have no device
+         * implementation. */
         const uint64_t model_ptr[3] = { h.model_bremsstrahlung,
                 h.model_pair_production, h.model_photonuclear };
-        const char * expected[3] = { "SSR", "SSR", "DRSS" };
+        const char * known[3][3] = { { "SSR", "KKP", "ABB" },
+                { "SSR", "KKP", nullptr }, { "DRSS", "BM", "BBKS" } };
         for (int i = 0; i < 3; i++) {
                 const size_t o = off(model_ptr[i], 1);
                 if (!ok) break;
@@ -252,10 +271,15 @@ inline int load_physics_bytes(
                     reinterpret_cast<const char *>(blob + o),
                     strnlen(reinterpret_cast<const char *>(blob + o),
                         size - o));
-                if (hp.model[i] != expected[i]) {
+                hp.model_index[i] = -1;
+                for (int k = 0; k < 3; k++)
+                        if ((known[i][k] != nullptr) &&
+                            (hp.model[i] == known[i][k]))
+                                hp.model_index[i] = k;
+                if (hp.model_index[i] < 0) {
                         err = "unsupported DCS model `" + hp.model[i] +
-                            "' (the device engine implements the defaults "
-                            "SSR/SSR/DRSS only)";
+                            "' (user registered models have no device "
+                            "implementation)";
                         return 14; /* PUMAS_RETURN_MODEL_ERROR */
                 }
         }
@@ -376,6 +400,8 @@ inline int load_physics_bytes(
         v.max_components = h.max_components;
         v.n_table_dcs = h.n_table_dcs;
         v.particle = h.particle;
+        for (int i = 0; i < 3; i++) v.model[i] = hp.model_index[i];
+        v.pad_ = 0;
         v.ctau = h.ctau;
         v.mass = h.mass;
         v.cutoff = h.cutoff;

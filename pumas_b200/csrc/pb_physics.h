@@ -33,6 +33,8 @@ struct Element {
         double z23;               /* pow(Z, 2. / 3.)   pumas.c:14434 */
         double Dn;                /* 1.54 * pow(A, 0.27) pumas.c:13943, 14418 */
         double lnA;               /* log(A)            pumas.c:14694 */
+        double a13;               /* pow(A, 1. / 3.)   pumas.c:14738, 14803, 15247 */
+        double wood_saxon;        /* dcs_wood_saxon(Z, A) pumas.c:14732-14748 */
 };
 
 struct Physics {
@@ -44,6 +46,10 @@ struct Physics {
         int max_components;
         int n_table_dcs;
         int particle;
+        /* DCS models the tables were built with (pb_dcs_models.h): [0]
+         * bremsstrahlung, [1] pair production, [2] photonuclear */
+        int model[3];
+        int pad_;
         double ctau;
         double mass;
         double cutoff;

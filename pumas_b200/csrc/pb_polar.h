@@ -75,12 +75,13 @@ PB_NOINLINE double polar_bremsstrahlung(
 
 /* Objective of the photonuclear maximisation, pumas.c:11855-11862. */
 struct PhotonuclearObjective {
+        const Physics * p;
         const Element * el;
         double ml, K, q;
         PB_FN double operator()(double lnQ2) const
         {
                 const double Q2 = xexp(lnQ2);
-                return -dcs_photonuclear_d2_DRSS(*el, ml, K, q, Q2) * Q2;
+                return -dcs_photonuclear_d2(*p, *el, ml, K, q, Q2) * Q2;
         }
 };
 
@@ -232,6 +233,7 @@ PB_NOINLINE double polar_photonuclear(
         PhotonuclearObjective objective;
         objective.el = &el;
         objective.ml = ml;
+        objective.p = &p;
         objective.K = ki;
         objective.q = q;
 
@@ -265,7 +267,7 @@ PB_NOINLINE double polar_photonuclear(
                 const double u = rng.uniform();
                 Q2 = Q2min * xexp(rQ2 * u);
                 const double r =
-                    dcs_photonuclear_d2_DRSS(el, ml, ki, q, Q2) * Q2;
+                    dcs_photonuclear_d2(p, el, ml, ki, q, Q2) * Q2;
                 if (rng.uniform() * fopt <= r) break;
         }
         if (i == 100) return 0.;

@@ -25,6 +25,8 @@ N_TRACKS = {
     "csda_spectrum_bwd": 20000, "mixed_loss": 20000,
     "mixed_loss_scattering": 2000, "mixed_loss_bwd": 4000,
     "csda_magnet_fwd": 20000, "csda_magnet_bwd": 20000,
+    "models_kkb_fwd": 3000, "models_kkb_bwd": 3000, "models_abm_fwd": 3000,
+    "models_abm_bwd": 3000,
     "geometry_detailed": 4000, "geometry_fast": 20000, "layers_check": 2000,
     "decay_randomised": 2000, "no_loss": 1500, "tau_ice": 20000,
     "above_grid": 4000, "above_grid_mixed": 20000, "vertex_stop": 20000, "vertex_stop_bwd": 20000, "limits_all": 6000,

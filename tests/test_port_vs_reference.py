@@ -52,6 +52,27 @@ def test_bit_exact(name):
     port.lib.port_set_specialise(1)
 
 
+@pytest.mark.parametrize("dump, n_elements", [
+    ("materials.muon", 6), ("rock.muon.kkb", 3), ("rock.muon.abm", 3)])
+def test_dcs_models_bit_exact(dump, n_elements):
+    """dcs_evaluate and the exact DCS model of every process, for the default
+    models (SSR / SSR / DRSS) and the others (KKP / KKP / BBKS and
+    ABB / SSR / BM, pb_dcs_models.h)."""
+    oracle, port, port_dd = sides(dump)
+    rng = np.random.default_rng(7)
+    for process in range(4):
+        for element in range(n_elements):
+            for _ in range(300):
+                k = float(np.exp(rng.uniform(np.log(1e-2), np.log(1e8))))
+                q = float(k * np.exp(rng.uniform(np.log(1e-4), 0.)))
+                for f in ("dcs_evaluate", "dcs_model"):
+                    a = getattr(oracle.lib, "oracle_" + f)(
+                        oracle.physics, process, element, k, q)
+                    b = getattr(port.lib, "port_" + f)(
+                        port.physics, process, element, k, q)
+                    assert a == b, (f, process, element, k, q, a, b)
+
+
 def test_unit_functions_bit_exact():
     """dcs_evaluate, the exact DCS models, msc and hard-elastic lookups."""
     oracle, port, port_dd = sides("materials.muon")

@@ -248,6 +248,25 @@ def above_grid(material, n, seed=0, energy_loss=MODE_STRAGGLED):
         states=make_states(n, log_uniform(n, 5e8, 1e11, seed)))
 
 
+def dcs_models(material, n, seed=0, direction=MODE_FORWARD,
+               medium="StandardRock"):
+    """Physics built with non-default DCS models (pb_dcs_models.h): hard
+    losses over five decades of energy, where the tabulated DCS falls back to
+    the model (pumas.c:11279-11346) and the photonuclear polar angle is drawn
+    from the model's doubly differential cross-section (pumas.c:11920)."""
+    k = log_uniform(n, 1., 1e5, seed)
+    limit = dict(limit_distance=300.)
+    event = EVENT_LIMIT_DISTANCE
+    if direction == MODE_BACKWARD:
+        limit["limit_energy"] = 1e7
+        event |= EVENT_LIMIT_ENERGY
+    return dict(
+        settings=make_settings(MODE_STRAGGLED, MODE_MIXED, direction=direction,
+                               event=event, **limit),
+        geometry=uniform_geometry(material(medium)),
+        states=make_states(n, k, direction=isotropic(n, seed + 1)))
+
+
 # name -> (dump, builder, kwargs)
 WORKLOADS = {
     "headline": ("materials.muon", headline, {}),
@@ -261,6 +280,12 @@ WORKLOADS = {
     "csda_magnet_fwd": ("materials.muon", csda_magnet, {}),
     "csda_magnet_bwd": ("materials.muon", csda_magnet,
                         dict(direction=MODE_BACKWARD)),
+    "models_kkb_fwd": ("rock.muon.kkb", dcs_models, {}),
+    "models_kkb_bwd": ("rock.muon.kkb", dcs_models,
+                       dict(direction=MODE_BACKWARD, medium="Water")),
+    "models_abm_fwd": ("rock.muon.abm", dcs_models, dict(medium="Water")),
+    "models_abm_bwd": ("rock.muon.abm", dcs_models,
+                       dict(direction=MODE_BACKWARD)),
     "rock_3km": ("materials.muon", rock_3km, {}),
     "mixed_loss": ("materials.muon", mixed_loss, {}),
     "mixed_loss_scattering": ("materials.muon", mixed_loss,
