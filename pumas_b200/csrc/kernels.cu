@@ -5,6 +5,8 @@
  *     path for any configuration;
  *   specialised instantiations of the same template for the common
  *     configurations live in kernels_spec*.cu and are tried first;
+ *   transport_csda_kernel (kernels_csda.cu): closed form CSDA in a uniform
+ *     medium, one thread per track, HBM bound;
  *   transport_kernel: one thread runs one track to completion; kept for A/B
  *     parity and profiling (divergence: 10.4 of 32 lanes active,
  *     profiles/r1_v0).
@@ -48,6 +50,7 @@ PB_SPECIALISATION(launch_spec_straggled_mixed_forward);
 PB_SPECIALISATION(launch_spec_straggled_mixed_backward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_forward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_backward);
+PB_SPECIALISATION(launch_spec_csda);
 
 cudaError_t transport_workspace_bytes(size_t * bytes)
 {
@@ -76,6 +79,7 @@ cudaError_t launch_transport(const Physics & p, const Settings & cfg,
         if (NAME(p, cfg, geo, seed, offset, n, states, events, media, status,  \
                 n_random, n_steps, workspace, stream, &e))                     \
                 return e;
+                TRY(launch_spec_csda)
                 TRY(launch_spec_straggled_mixed_forward)
                 TRY(launch_spec_straggled_mixed_backward)
                 TRY(launch_spec_straggled_noscat_forward)
