@@ -44,7 +44,7 @@
 namespace pb {
 
 #ifndef PB_RS_WARPS
-#define PB_RS_WARPS 16
+#define PB_RS_WARPS 12
 #endif
 #ifndef PB_RS_DEL_WARPS
 #define PB_RS_DEL_WARPS 1
@@ -328,18 +328,11 @@ __device__ __forceinline__ void park_load(Resident & s, RingRng & rng,
         rng.seek(offset + (ix & 0x00ffffffffffffffull), (uint32_t)(c >> 32));
 }
 
-/* Exchange the track of a lane with a parked one in place (the lane has a
- * pending event and takes over a track whose event has been served). */
-template <int STRIDE>
-__device__ __forceinline__ void park_swap(Resident & s, RingRng & rng,
-    uint64_t offset, unsigned long long * words, int e)
+/* Unpack the words of a parked track into a lane and position the random
+ * stream on it. */
+__device__ __forceinline__ void park_unpack(Resident & s, RingRng & rng,
+    uint64_t offset, const unsigned long long (&in)[RS_PARK_WORDS])
 {
-        /* the incoming track: all loads in flight together */
-        unsigned long long in[RS_PARK_WORDS];
-#pragma unroll
-        for (int k = 0; k < RS_PARK_WORDS; k++) in[k] = PARK_W(k);
-        park_store<STRIDE>(s, rng, offset, words, e);
-
         State & st = s.state;
         Track & t = s.trk;
         Loop & l = s.lp;
@@ -389,6 +382,36 @@ __device__ __forceinline__ void park_swap(Resident & s, RingRng & rng,
         t.n_steps = (uint32_t)c;
         t.iK = (int)(ix >> 56);
         rng.seek(offset + (ix & 0x00ffffffffffffffull), (uint32_t)(c >> 32));
+}
+
+/* Exchange the track of a lane with a parked one in place (the lane has a
+ * pending event and takes over a track whose event has been served). */
+template <int STRIDE>
+__device__ __forceinline__ void park_swap(Resident & s, RingRng & rng,
+    uint64_t offset, unsigned long long * words, int e)
+{
+        /* the incoming track: all loads in flight together */
+        unsigned long long in[RS_PARK_WORDS];
+#pragma unroll
+        for (int k = 0; k < RS_PARK_WORDS; k++) in[k] = PARK_W(k);
+        park_store<STRIDE>(s, rng, offset, words, e);
+        park_unpack(s, rng, offset, in);
+}
+/* One copy of the load / store / unpack code for the call sites where lanes
+ * do different things (the hot code must stay small, see the header): a lane
+ * that `takes` the parked track of entry e loads it, a lane that `leaves` its
+ * own track there stores it; both = an exchange in place. */
+template <int STRIDE>
+__device__ __forceinline__ void park_exchange(Resident & s, RingRng & rng,
+    uint64_t offset, unsigned long long * words, int e, bool takes, bool leaves)
+{
+        /* (a lane that only leaves reads the vacant entry for nothing: an
+         * unconditional load keeps the words in registers) */
+        unsigned long long in[RS_PARK_WORDS];
+#pragma unroll
+        for (int k = 0; k < RS_PARK_WORDS; k++) in[k] = PARK_W(k);
+        if (leaves) park_store<STRIDE>(s, rng, offset, words, e);
+        if (takes) park_unpack(s, rng, offset, in);
 }
 #undef PARK_W
 #undef PARK_ST
@@ -554,13 +577,17 @@ static_assert(N_RSTATS <= N_STATS, "statistics buffer");
 constexpr size_t RS_PARK_BYTES =
     (size_t)RS_PARK_WORDS * RS_ENTRIES * sizeof(unsigned long long);
 
+/* (A template on the CTA size: translation units may be built with different
+ * PB_RS_WARPS, see kernels_spec2.cu, and each needs its own host copy.) */
+template <int WARPS>
 __host__ __device__ constexpr size_t resident_smem_bytes(bool pooled)
 {
         return ((sizeof(ResidentShared) + 15) & ~(size_t)15) +
             3 * RS_ENTRIES * sizeof(unsigned short) +
-            (size_t)RS_RING_WORDS * RS_THREADS * sizeof(uint32_t) +
-            (size_t)RS_WARPS * N_RSTATS * sizeof(unsigned long long) +
-            RS_PARK_BYTES + (pooled ? RS_POOL_BYTES * RS_STEP_WARPS : 0);
+            (size_t)RS_RING_WORDS * (32 * WARPS) * sizeof(uint32_t) +
+            (size_t)WARPS * N_RSTATS * sizeof(unsigned long long) +
+            RS_PARK_BYTES +
+            (pooled ? RS_POOL_BYTES * (WARPS - RS_DEL_WARPS) : 0);
 }
 
 /* Do hard elastic events go through the warp pools? */
@@ -572,8 +599,9 @@ template <class Cfg> __host__ __device__ inline bool resident_pooled(const Cfg &
 
 template <class Cfg, class Geo>
 __global__ void __launch_bounds__(RS_THREADS, 1)
-    transport_resident_kernel(const Physics p, const Cfg cfg, const Geo geo,
-        const BatchArgs a)
+    transport_resident_kernel(const __grid_constant__ Physics p,
+        const __grid_constant__ Cfg cfg, const __grid_constant__ Geo geo,
+        const __grid_constant__ BatchArgs a)
 {
         extern __shared__ __align__(16) unsigned char smem_raw[];
         const int lane = threadIdx.x & 31;
@@ -634,12 +662,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                 if (lane == 0) wstat[k] += v_;                                 \
         }
 
-        Resident s;
-        RingRng rng;
-        rng.attach(rings + threadIdx.x, a.seed);
-
         if (warp >= RS_STEP_WARPS) {
-                /* ---- DEL warp: hard inelastic events of the whole CTA ---- */
+                /* ---- DEL warp: hard inelastic events of the whole CTA ----
+                 * (its own track and stream objects: the out-of-line DCS and
+                 * polar angle code takes them by reference, which pins them
+                 * to local memory; the stepping warps' must stay in
+                 * registers) */
+                Resident s;
+                RingRng rng;
+                rng.attach(rings + threadIdx.x, a.seed);
                 int idle = 0;
                 for (;;) {
                         const int avail = ring_available(&sh.del_);
@@ -696,6 +727,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                 }
         } else {
                 /* ---- stepping warp ---------------------------------------- */
+                Resident s;
+                RingRng rng;
+                rng.attach(rings + threadIdx.x, a.seed);
                 int phase = PHASE_EMPTY;
                 bool exhausted = false;
                 const unsigned int lt_mask = (1u << lane) - 1u;
@@ -750,28 +784,17 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                         unsigned int to_pending = 0;
                                         unsigned int to_vacant = 0;
                                         if (e >= 0) {
-                                                if (swap && ehs) {
-                                                        park_swap<
-                                                            RS_POOL_STRIDE>(s,
-                                                            rng, a.offset,
-                                                            pool, e);
-                                                        phase = PHASE_STEP;
+                                                /* swap && ehs: exchange;
+                                                 * swap: take; else: leave */
+                                                park_exchange<RS_POOL_STRIDE>(
+                                                    s, rng, a.offset, pool, e,
+                                                    swap, ehs);
+                                                phase = swap ? PHASE_STEP :
+                                                               PHASE_EMPTY;
+                                                if (ehs)
                                                         to_pending = 1u << e;
-                                                } else if (swap) {
-                                                        park_load<
-                                                            RS_POOL_STRIDE>(s,
-                                                            rng, a.offset,
-                                                            pool, e);
-                                                        phase = PHASE_STEP;
+                                                else
                                                         to_vacant = 1u << e;
-                                                } else {
-                                                        park_store<
-                                                            RS_POOL_STRIDE>(s,
-                                                            rng, a.offset,
-                                                            pool, e);
-                                                        phase = PHASE_EMPTY;
-                                                        to_pending = 1u << e;
-                                                }
                                         }
                                         RS_STAT(RSTAT_WAITS,
                                             __popc(__ballot_sync(RS_FULL,
@@ -924,12 +947,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 const bool in_place = (phase == PHASE_EHS);
                                 const bool swap = mine && (phase == PHASE_STEP);
                                 const bool load = mine && (phase == PHASE_EMPTY);
-                                if (swap)
-                                        park_swap<RS_POOL_STRIDE>(
-                                            s, rng, a.offset, pool, lane);
-                                else if (load)
-                                        park_load<RS_POOL_STRIDE>(
-                                            s, rng, a.offset, pool, lane);
+                                if (swap || load)
+                                        park_exchange<RS_POOL_STRIDE>(s, rng,
+                                            a.offset, pool, lane, true, swap);
                                 const unsigned int m_swap =
                                     __ballot_sync(RS_FULL, swap);
                                 const unsigned int m_load =
@@ -1011,7 +1031,8 @@ cudaError_t launch_resident(const Physics & p, const Cfg & cfg, const Geo & geo,
 {
         static size_t ready = 0; /* per instantiation: opted-in size */
         const Tunables & t = tunables();
-        const size_t smem = resident_smem_bytes(resident_pooled(cfg));
+        const size_t smem =
+            resident_smem_bytes<RS_WARPS>(resident_pooled(cfg));
         cudaError_t e;
         if (ready < smem) {
                 e = cudaFuncSetAttribute(transport_resident_kernel<Cfg, Geo>,
