@@ -114,6 +114,8 @@ struct BatchArgs {
         unsigned int * n_random;
         unsigned int * n_steps;
         unsigned long long * cursor; /* global work cursor (workspace) */
+        unsigned char * workspace;   /* WORKSPACE_BYTES of global scratch */
+        int n_del_ctas; /* CTAs serving the hard inelastic events (offload) */
         unsigned long long * stats;  /* optional scheduler statistics */
         int ehs_period;    /* the warp pools are served every that many rounds */
         int del_threshold; /* events queued before a DEL warp starts a pass */
@@ -126,13 +128,14 @@ constexpr int N_STATS = 16;
 struct Tunables {
         int ehs_period, del_threshold; /* <= 0: the kernel's default */
         int grid_cap;                  /* <= 0: one CTA per SM */
+        int del_ctas;                  /* <= 0: the launcher's choice */
         unsigned long long * stats;
         int sms;
 };
 
 inline const Tunables & tunables()
 {
-        static Tunables t = { 0, 0, 0, nullptr, 0 };
+        static Tunables t = { 0, 0, 0, 0, nullptr, 0 };
         if (t.sms != 0) return t;
         const char * v;
         if ((v = getenv("PUMAS_B200_EHS_PERIOD")) != nullptr)
@@ -140,6 +143,8 @@ inline const Tunables & tunables()
         if ((v = getenv("PUMAS_B200_DEL_THRESHOLD")) != nullptr)
                 t.del_threshold = atoi(v);
         if ((v = getenv("PUMAS_B200_GRID")) != nullptr) t.grid_cap = atoi(v);
+        if ((v = getenv("PUMAS_B200_DEL_CTAS")) != nullptr)
+                t.del_ctas = atoi(v);
         if (getenv("PUMAS_B200_STATS") != nullptr)
                 cudaMalloc(&t.stats, N_STATS * sizeof *t.stats);
         int dev = 0;
@@ -148,8 +153,11 @@ inline const Tunables & tunables()
         return t;
 }
 
-/* The workspace holds the global work cursor. */
-inline size_t workspace_bytes() { return 256; }
+/* The workspace holds the global work cursor and, for the kernels that hand
+ * the hard inelastic events over to dedicated CTAs (resident.cuh,
+ * PB_RS_OFFLOAD), their queues and parking area. */
+constexpr size_t WORKSPACE_BYTES = (size_t)4 << 20;
+inline size_t workspace_bytes() { return WORKSPACE_BYTES; }
 
 } /* namespace pb */
 

@@ -4,6 +4,8 @@
  * locals (examples/pumas/straight.c geometry). Same source as the general
  * kernel (resident.cuh); only unreachable code is removed.
  */
+/* Hard inelastic events served by dedicated CTAs (resident.cuh). */
+#define PB_RS_OFFLOAD 1
 #include "resident.cuh"
 
 namespace pb {

@@ -40,6 +40,12 @@
 #define PB_RESIDENT_CUH
 
 #include "device_common.cuh"
+#ifdef PB_RS_DEBUG
+#include <cassert>
+#define RS_ASSERT(x) assert(x)
+#else
+#define RS_ASSERT(x)
+#endif
 
 namespace pb {
 
@@ -57,6 +63,21 @@ namespace pb {
 #define PB_RS_LOCKSTEP 1
 #endif
 #define RS_FENCE() __threadfence_block()
+/* 1: the hard inelastic events are served by dedicated CTAs (the first
+ * `n_del_ctas` of the grid) instead of by the DEL warp of each CTA. The DCS
+ * models, the polar angle samplers and the Brent maximiser are ~500 KB of cold
+ * code: run on the same SM they evict the stepping loop from the instruction
+ * cache, and no_instruction is the first stall reason of this kernel (timing
+ * experiment without hard inelastic events: +24 % steps/s). The stepping
+ * warps work as before, through the queues and the parking area of their CTA
+ * in shared memory; the CTA's last warp becomes a *courier* that moves parked
+ * tracks between them and global queues in the workspace, out of the lockstep
+ * rounds (a global queue operation is several microseconds of dependent L2
+ * round trips). A served track returns to whichever CTA asks first. Set per
+ * translation unit (kernels_spec0.cu, kernels_spec1.cu). */
+#ifndef PB_RS_OFFLOAD
+#define PB_RS_OFFLOAD 0
+#endif
 #ifndef PB_RS_TIMING
 #define PB_RS_TIMING 0
 #endif
@@ -104,6 +125,25 @@ constexpr int PHASE_EMPTY = 4;
 static_assert((RS_ENTRIES & (RS_ENTRIES - 1)) == 0, "power of two");
 static_assert(RS_ENTRIES < RS_NONE, "16 bit entry indices");
 static_assert(RS_STEP_WARPS > 0, "no stepping warp");
+constexpr bool RS_OFFLOAD = (PB_RS_OFFLOAD != 0);
+static_assert(!RS_OFFLOAD || (RS_DEL_WARPS == 1), "one courier warp");
+static_assert(!RS_OFFLOAD || (PB_RS_LOCKSTEP != 0), "offload needs lockstep");
+/* entries of the global parking area (offload), power of two */
+constexpr int RS_GENTRIES = 8192;
+/* A lane that parks a track without taking a served one in exchange goes on
+ * with a fresh track: one more track in flight, and without a limit the parked
+ * population grows until every entry, global and shared, holds a track
+ * (observed). No fresh track is taken while fewer than that many global
+ * entries are free. */
+constexpr int RS_INTAKE_LEVEL = RS_GENTRIES / 2;
+/* Free entries of a CTA's parking area the stepping lanes leave to the courier
+ * for the tracks that come back (it keeps at most 16 waiting). With them a
+ * served track can always enter some CTA, a lane with a pending event can
+ * always exchange its track for one that waits, and an exchange frees a
+ * global entry for the next pending event: the queues cannot dead lock, even
+ * with every global entry taken. */
+constexpr int RS_INBOUND_RESERVE = 32;
+static_assert(RS_GENTRIES < RS_NONE, "16 bit entry indices");
 
 /* Philox stream of one track through a per thread ring in shared memory.
  * `count` words have been consumed, words [count, filled) are in the ring. */
@@ -421,11 +461,12 @@ struct Ring {
         unsigned int head, tail;
 };
 
+template <int ENTRIES = RS_ENTRIES>
 __device__ __forceinline__ void ring_push(
     volatile unsigned short * slots, Ring * r, int e)
 {
         const unsigned int pos = atomicAdd(&r->tail, 1u);
-        slots[pos & (RS_ENTRIES - 1)] = (unsigned short)e;
+        slots[pos & (ENTRIES - 1)] = (unsigned short)e;
 }
 
 __device__ __forceinline__ int ring_available(const Ring * r)
@@ -437,8 +478,9 @@ __device__ __forceinline__ int ring_available(const Ring * r)
 
 /* Pop one index for each lane that wants one, as many as there are. Called by
  * the 32 lanes of a warp together. Returns the index, or -1. */
-__device__ __forceinline__ int ring_pop_warp(
-    volatile unsigned short * slots, Ring * r, bool want, int lane)
+template <int ENTRIES = RS_ENTRIES>
+__device__ __forceinline__ int ring_pop_warp(volatile unsigned short * slots,
+    Ring * r, bool want, int lane, int reserve = 0)
 {
         const unsigned int m = __ballot_sync(RS_FULL, want);
         if (m == 0) return -1;
@@ -449,7 +491,7 @@ __device__ __forceinline__ int ring_pop_warp(
                 for (;;) {
                         h = *(volatile unsigned int *)&r->head;
                         const unsigned int t = *(volatile unsigned int *)&r->tail;
-                        n = (int)(t - h);
+                        n = (int)(t - h) - reserve;
                         if (n > k) n = k;
                         if (n <= 0) {
                                 n = 0;
@@ -464,7 +506,7 @@ __device__ __forceinline__ int ring_pop_warp(
         const int rank = __popc(m & ((1u << lane) - 1u));
         int e = -1;
         if (want && (rank < n)) {
-                const unsigned int at = (h + (unsigned int)rank) & (RS_ENTRIES - 1);
+                const unsigned int at = (h + (unsigned int)rank) & (ENTRIES - 1);
                 do {
                         e = slots[at];
                 } while (e == RS_NONE);
@@ -546,6 +588,8 @@ struct ResidentShared {
         int live;      /* tracks taken by this CTA and not flushed yet */
         int exhausted; /* the global cursor ran out */
         int stop[2];
+        int over; /* (offload) every track of the batch has been flushed */
+        int may_intake; /* (offload) the global parking area has room */
 };
 
 constexpr size_t RS_POOL_BYTES =
@@ -576,6 +620,225 @@ static_assert(N_RSTATS <= N_STATS, "statistics buffer");
  * for the physics tables and the register spills. */
 constexpr size_t RS_PARK_BYTES =
     (size_t)RS_PARK_WORDS * RS_ENTRIES * sizeof(unsigned long long);
+
+/* Layout of the global workspace in offload mode (device_common.cuh:
+ * WORKSPACE_BYTES). */
+struct OffloadHeader {
+        unsigned long long cursor; /* (first: BatchArgs::cursor) */
+        int live;                  /* tracks taken and not flushed, all CTAs */
+        int pad_;
+        Ring free_, del_, ret_;
+};
+constexpr size_t RS_OFFLOAD_QUEUES = 256; /* byte offset of the queues */
+constexpr size_t RS_OFFLOAD_PARK =
+    RS_OFFLOAD_QUEUES + 3 * (size_t)RS_GENTRIES * sizeof(unsigned short);
+constexpr size_t RS_GPARK_BYTES =
+    (size_t)RS_PARK_WORDS * RS_GENTRIES * sizeof(unsigned long long);
+static_assert(sizeof(OffloadHeader) <= RS_OFFLOAD_QUEUES, "header");
+static_assert(RS_OFFLOAD_PARK + RS_GPARK_BYTES <= WORKSPACE_BYTES,
+    "workspace too small");
+
+/* The queues of the global workspace, as a kernel sees them. */
+struct OffloadQueues {
+        OffloadHeader * h;
+        volatile unsigned short * free_q, * del_q, * ret_q;
+        unsigned long long * park;
+
+        __device__ __forceinline__ explicit OffloadQueues(unsigned char * w)
+        {
+                h = reinterpret_cast<OffloadHeader *>(w);
+                free_q = reinterpret_cast<volatile unsigned short *>(
+                    w + RS_OFFLOAD_QUEUES);
+                del_q = free_q + RS_GENTRIES;
+                ret_q = del_q + RS_GENTRIES;
+                park = reinterpret_cast<unsigned long long *>(
+                    w + RS_OFFLOAD_PARK);
+        }
+        /* Changes whenever anything moves (watchdogs). */
+        __device__ __forceinline__ unsigned long long progress() const
+        {
+                return *(volatile unsigned long long *)&h->cursor * 1000003ull +
+                    (unsigned long long)(unsigned int)*(volatile int *)&h
+                            ->live *
+                        7919ull +
+                    *(volatile unsigned int *)&h->del_.tail +
+                    *(volatile unsigned int *)&h->ret_.tail * 31ull;
+        }
+        /* Every track has been taken from the cursor ... */
+        __device__ __forceinline__ bool all_taken(const BatchArgs & a) const
+        {
+                return *(volatile unsigned long long *)&h->cursor >=
+                    (unsigned long long)a.n;
+        }
+        /* ... and flushed. (A taker adds to `live` before it advances the
+         * cursor: the cursor is read first.) */
+        __device__ __forceinline__ bool all_over(const BatchArgs & a) const
+        {
+                if (!all_taken(a)) return false;
+                __threadfence();
+                return *(volatile int *)&h->live == 0;
+        }
+};
+
+/* Prepares the workspace for one launch. */
+static __global__ void resident_offload_init(unsigned char * workspace)
+{
+        OffloadHeader * const h = reinterpret_cast<OffloadHeader *>(workspace);
+        unsigned short * const q =
+            reinterpret_cast<unsigned short *>(workspace + RS_OFFLOAD_QUEUES);
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i == 0) {
+                h->cursor = 0;
+                h->live = 0;
+                h->free_.head = 0;
+                h->free_.tail = RS_GENTRIES;
+                h->del_.head = h->del_.tail = 0;
+                h->ret_.head = h->ret_.tail = 0;
+        }
+        if (i < RS_GENTRIES) {
+                q[i] = (unsigned short)i;
+                q[RS_GENTRIES + i] = (unsigned short)RS_NONE;
+                q[2 * RS_GENTRIES + i] = (unsigned short)RS_NONE;
+        }
+}
+
+/* A value read by lane 0 for the whole warp: the decisions of the queue loops
+ * must be warp uniform (their queue operations are warp collectives), and two
+ * lanes that poll the same word at different times may see different values. */
+template <class F> __device__ __forceinline__ int warp_uniform(F f, int lane)
+{
+        __syncwarp();
+        int v = 0;
+        if (lane == 0) v = f();
+        return __shfl_sync(RS_FULL, v, 0);
+}
+
+/* The courier of a stepping CTA (offload): moves the tracks parked with a
+ * pending hard inelastic event from the CTA's shared memory to the global
+ * queue of the DEL CTAs, and served tracks back, whole warp, one track per
+ * lane. Returns when every track of the batch has been flushed. */
+__device__ __forceinline__ void courier_loop(const BatchArgs & a,
+    ResidentShared & sh, volatile unsigned short * free_q,
+    volatile unsigned short * del_q, volatile unsigned short * ret_q,
+    unsigned long long * park, int lane)
+{
+        const OffloadQueues g(a.workspace);
+        long still = 0; /* watchdog: a stuck queue fails loudly */
+        int stalled = 0;
+        unsigned long long last_sig = 0;
+        for (;;) {
+                bool moved = false;
+                /* outbound: pending events */
+                const int out = warp_uniform(
+                    [&]() { return ring_available(&sh.del_); }, lane);
+                if (out > 0) {
+                        /* a global entry first, without waiting for one (a
+                         * courier that waited here while every entry holds a
+                         * served track nobody fetches would be a deadlock);
+                         * then the event: this warp is the only consumer of
+                         * the CTA's queue, what it saw is still there */
+                        const int eg = ring_pop_warp<RS_GENTRIES>(
+                            g.free_q, &g.h->free_, lane < out, lane);
+                        const int es = ring_pop_warp(
+                            del_q, &sh.del_, eg >= 0, lane);
+                        if (eg >= 0) {
+                                RS_ASSERT(es >= 0);
+                                __threadfence_block();
+#pragma unroll
+                                for (int k = 0; k < RS_PARK_WORDS; k++)
+                                        ParkMem::st(
+                                            &g.park[k * RS_GENTRIES + eg],
+                                            ParkMem::ld(
+                                                &park[k * RS_ENTRIES + es]));
+                                __threadfence();
+                                ring_push<RS_GENTRIES>(
+                                    g.del_q, &g.h->del_, eg);
+                                ring_push(free_q, &sh.free_, es);
+                                moved = true;
+                        }
+                }
+                /* inbound: served tracks, as long as the CTA has lanes that
+                 * may want them (few waiting in shared memory) and room */
+                const int in = warp_uniform(
+                    [&]() {
+                            const int waiting = ring_available(&sh.ret_);
+                            const int room = ring_available(&sh.free_);
+                            if ((waiting >= 16) || (room <= 0)) return 0;
+                            int n = ring_available(&g.h->ret_);
+                            if (n > room) n = room;
+                            if (n > 16 - waiting) n = 16 - waiting;
+                            return n;
+                    },
+                    lane);
+                {
+                        if (in > 0) {
+                                int eg = ring_pop_warp<RS_GENTRIES>(
+                                    g.ret_q, &g.h->ret_, lane < in, lane);
+                                const int es = ring_pop_warp(
+                                    free_q, &sh.free_, eg >= 0, lane);
+                                if ((eg >= 0) && (es < 0)) {
+                                        /* the stepping warps took the room:
+                                         * give the track back */
+                                        ring_push<RS_GENTRIES>(
+                                            g.ret_q, &g.h->ret_, eg);
+                                        eg = -1;
+                                }
+                                if (eg >= 0) {
+                                        __threadfence();
+#pragma unroll
+                                        for (int k = 0; k < RS_PARK_WORDS; k++)
+                                                ParkMem::st(
+                                                    &park[k * RS_ENTRIES + es],
+                                                    ParkMem::ld(&g.park[k *
+                                                            RS_GENTRIES +
+                                                        eg]));
+                                        __threadfence_block();
+                                        ring_push(ret_q, &sh.ret_, es);
+                                        ring_push<RS_GENTRIES>(
+                                            g.free_q, &g.h->free_, eg);
+                                        moved = true;
+                                }
+                        }
+                }
+                /* the end of the batch, for the stepping warps of the CTA */
+                const int over = warp_uniform(
+                    [&]() {
+                            if (lane == 0)
+                                    *(volatile int *)&sh.may_intake =
+                                        (ring_available(&g.h->free_) >
+                                            RS_INTAKE_LEVEL) ?
+                                        1 :
+                                        0;
+                            return g.all_over(a) ? 1 : 0;
+                    },
+                    lane);
+                if (over) {
+                        if (lane == 0) *(volatile int *)&sh.over = 1;
+                        break;
+                }
+                if (!__any_sync(RS_FULL, moved)) __nanosleep(500);
+                still = __any_sync(RS_FULL, moved) ? 0 : still + 1;
+                if ((still > 0) && ((still & 0x1fffff) == 0)) {
+                        /* watchdog, as in the DEL CTAs */
+                        const unsigned long long sig = g.progress();
+                        stalled = (sig == last_sig) ? stalled + 1 : 0;
+                        last_sig = sig;
+                        if ((stalled >= 8) && (lane == 0)) {
+                                printf("[pumas_b200: courier of CTA %d] "
+                                       "stuck: sfree=%d sdel=%d sret=%d "
+                                       "gret=%d live=%d cursor=%llu\n",
+                                    (int)blockIdx.x, ring_available(&sh.free_),
+                                    ring_available(&sh.del_),
+                                    ring_available(&sh.ret_),
+                                    ring_available(&g.h->ret_),
+                                    *(volatile int *)&g.h->live,
+                                    *(volatile unsigned long long *)&g.h
+                                         ->cursor);
+                                __trap();
+                        }
+                }
+        }
+}
 
 /* (A template on the CTA size: translation units may be built with different
  * PB_RS_WARPS, see kernels_spec2.cu, and each needs its own host copy.) */
@@ -633,6 +896,8 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                 sh.ret_.head = sh.ret_.tail = 0;
                 sh.live = 0;
                 sh.exhausted = 0;
+                sh.over = 0;
+                sh.may_intake = 1;
                 sh.stop[0] = sh.stop[1] = 0;
                 for (int k = 0; k < N_SYNC_POINTS; k++)
                         asm volatile(
@@ -662,7 +927,37 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                 if (lane == 0) wstat[k] += v_;                                 \
         }
 
+#if PB_RS_OFFLOAD
+        /* the DEL CTAs serve the global queues with all their warps; a
+         * stepping CTA has a courier warp instead of a DEL warp */
+        const bool del_cta = ((int)blockIdx.x < a.n_del_ctas);
+        const OffloadQueues gq(a.workspace);
+        volatile unsigned short * const d_free_q = gq.free_q;
+        volatile unsigned short * const d_del_q = gq.del_q;
+        volatile unsigned short * const d_ret_q = gq.ret_q;
+        Ring * const d_free = &gq.h->free_;
+        Ring * const d_del = &gq.h->del_;
+        Ring * const d_ret = &gq.h->ret_;
+        unsigned long long * const d_park = gq.park;
+        int * const live = &gq.h->live;
+        constexpr int D_ENTRIES = RS_GENTRIES;
+#define RS_DEL_FENCE() __threadfence()
+        if (!del_cta && (warp >= RS_STEP_WARPS)) {
+                courier_loop(a, sh, free_q, del_q, ret_q, park, lane);
+        } else if (del_cta) {
+#else
+        volatile unsigned short * const d_free_q = free_q;
+        volatile unsigned short * const d_del_q = del_q;
+        volatile unsigned short * const d_ret_q = ret_q;
+        Ring * const d_free = &sh.free_;
+        Ring * const d_del = &sh.del_;
+        Ring * const d_ret = &sh.ret_;
+        unsigned long long * const d_park = park;
+        int * const live = &sh.live;
+        constexpr int D_ENTRIES = RS_ENTRIES;
+#define RS_DEL_FENCE() RS_FENCE()
         if (warp >= RS_STEP_WARPS) {
+#endif
                 /* ---- DEL warp: hard inelastic events of the whole CTA ----
                  * (its own track and stream objects: the out-of-line DCS and
                  * polar angle code takes them by reference, which pins them
@@ -672,21 +967,44 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                 RingRng rng;
                 rng.attach(rings + threadIdx.x, a.seed);
                 int idle = 0;
+#if PB_RS_OFFLOAD
+                int stalled = 0;
+                unsigned long long last_sig = 0;
+#endif
                 for (;;) {
-                        const int avail = ring_available(&sh.del_);
+#if PB_RS_OFFLOAD
+                        const int avail = warp_uniform(
+                            [&]() { return ring_available(d_del); }, lane);
+                        const int ending = warp_uniform(
+                            [&]() {
+                                    return gq.all_taken(a) ?
+                                        (gq.all_over(a) ? 2 : 1) :
+                                        0;
+                            },
+                            lane);
+                        const bool over_soon = (ending >= 1);
+                        const bool over = (ending >= 2);
+#else
+                        const int avail = ring_available(d_del);
                         const bool over_soon =
                             (*(volatile int *)&sh.exhausted != 0);
                         const bool over = over_soon &&
                             (*(volatile int *)&sh.live == 0);
+#endif
                         if ((avail >= a.del_threshold) ||
                             ((avail > 0) && ((idle >= 64) || over_soon))) {
-                                const int e = ring_pop_warp(
-                                    del_q, &sh.del_, lane < avail, lane);
+                                const int e = ring_pop_warp<D_ENTRIES>(
+                                    d_del_q, d_del, lane < avail, lane);
                                 int flushed = 0;
                                 if (e >= 0) {
-                                        RS_FENCE();
-                                        park_load<RS_ENTRIES>(
-                                            s, rng, a.offset, park, e);
+                                        RS_DEL_FENCE();
+                                        park_load<D_ENTRIES>(
+                                            s, rng, a.offset, d_park, e);
+                                        RS_ASSERT((s.lp.material >= 0) &&
+                                            (s.lp.material < 8));
+                                        RS_ASSERT((long)(rng.track() -
+                                                      a.offset) < a.n);
+                                        RS_ASSERT(s.trk.step_event != 0);
                                         rng.top_up();
                                         const int ph = stepping_del(p, cfg, geo,
                                             s.trk, rng, s.state, s.lp);
@@ -698,13 +1016,15 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                                     s.medium0;
                                                 track_end(s.trk, s.lp, out);
                                                 resident_flush(s, rng, out, a);
-                                                ring_push(free_q, &sh.free_, e);
+                                                ring_push<D_ENTRIES>(
+                                                    d_free_q, d_free, e);
                                                 flushed = 1;
                                         } else {
-                                                park_store<RS_ENTRIES>(
-                                                    s, rng, a.offset, park, e);
-                                                RS_FENCE();
-                                                ring_push(ret_q, &sh.ret_, e);
+                                                park_store<D_ENTRIES>(s, rng,
+                                                    a.offset, d_park, e);
+                                                RS_DEL_FENCE();
+                                                ring_push<D_ENTRIES>(
+                                                    d_ret_q, d_ret, e);
                                         }
                                 }
                                 const unsigned int got =
@@ -713,7 +1033,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                     __ballot_sync(RS_FULL, flushed != 0);
                                 if ((lane == 0) && (fl != 0)) {
                                         __threadfence();
-                                        atomicSub(&sh.live, __popc(fl));
+                                        atomicSub(live, __popc(fl));
                                 }
                                 RS_STAT(RSTAT_DEL_PASSES, 1)
                                 RS_STAT(RSTAT_DEL_LANES, __popc(got))
@@ -723,6 +1043,33 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                         } else {
                                 __nanosleep(1000);
                                 idle++;
+#if PB_RS_OFFLOAD
+                                /* watchdog: ~25 s without an event to serve
+                                 * while nothing moves anywhere in the batch
+                                 * is a stuck queue: fail loudly */
+                                if ((idle & 0xfffff) == 0) {
+                                        const unsigned long long sig =
+                                            gq.progress();
+                                        stalled =
+                                            (sig == last_sig) ? stalled + 1 : 0;
+                                        last_sig = sig;
+                                        if ((stalled >= 8) && (lane == 0) &&
+                                            (warp == 0)) {
+                                                printf("[pumas_b200: DEL CTA "
+                                                       "%d] stuck: live=%d "
+                                                       "cursor=%llu gfree=%d "
+                                                       "gdel=%d gret=%d\n",
+                                                    (int)blockIdx.x,
+                                                    *(volatile int *)live,
+                                                    *(volatile unsigned long long
+                                                            *)a.cursor,
+                                                    ring_available(d_free),
+                                                    ring_available(d_del),
+                                                    ring_available(d_ret));
+                                                __trap();
+                                        }
+                                }
+#endif
                         }
                 }
         } else {
@@ -843,8 +1190,16 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                         phase = PHASE_STEP;
                                 }
                                 const bool del_2 = (phase == PHASE_DEL);
+#if PB_RS_OFFLOAD
+                                /* (the last free entries of the CTA are kept
+                                 * for the tracks that come back: see
+                                 * RS_INBOUND_RESERVE) */
+                                e = ring_pop_warp(free_q, &sh.free_, del_2,
+                                    lane, RS_INBOUND_RESERVE);
+#else
                                 e = ring_pop_warp(
                                     free_q, &sh.free_, del_2, lane);
+#endif
                                 if (e >= 0) {
                                         park_store<RS_ENTRIES>(
                                             s, rng, a.offset, park, e);
@@ -869,13 +1224,27 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 }
 
                                 /* then fresh ones from the global cursor */
+#if PB_RS_OFFLOAD
+                                /* (no new track while the global parking area
+                                 * is half full: the lanes wait for served
+                                 * ones; the courier watches the level) */
+                                const unsigned int m = __ballot_sync(RS_FULL,
+                                    (phase == PHASE_EMPTY) &&
+                                        (*(volatile int *)&sh.may_intake !=
+                                            0));
+#else
                                 const unsigned int m = __ballot_sync(
                                     RS_FULL, phase == PHASE_EMPTY);
+#endif
                                 if ((m != 0) && !exhausted) {
                                         const int k = __popc(m);
                                         long base = 0;
                                         if (lane == 0) {
-                                                atomicAdd(&sh.live, k);
+                                                atomicAdd(live, k);
+#if PB_RS_OFFLOAD
+                                                /* (other CTAs read the two) */
+                                                __threadfence();
+#endif
                                                 base = (long)atomicAdd(a.cursor,
                                                     (unsigned long long)k);
                                         }
@@ -893,6 +1262,7 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                         const int rank = __popc(m & lt_mask);
                                         bool early = false;
                                         if ((phase == PHASE_EMPTY) &&
+                                            (((m >> lane) & 1u) != 0) &&
                                             (rank < got)) {
                                                 const long i = base + rank;
                                                 s.state = a.states[i];
@@ -914,17 +1284,26 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
                                 }
                                 if ((gone > 0) && (lane == 0)) {
                                         __threadfence();
-                                        atomicSub(&sh.live, gone);
+                                        atomicSub(live, gone);
                                 }
                         }
 
                         RS_TICK(RSTAT_T_SERVICE)
                         /* the end: no track left in this CTA, none to take */
 #if PB_RS_LOCKSTEP
+#if PB_RS_OFFLOAD
+                        /* (tracks come back from the DEL CTAs to any stepping
+                         * CTA: everybody stays until the last one is flushed,
+                         * which the courier watches) */
+                        if (threadIdx.x == 0)
+                                *(volatile int *)&sh.stop[round & 1] =
+                                    *(volatile int *)&sh.over;
+#else
                         if (threadIdx.x == 0)
                                 *(volatile int *)&sh.stop[round & 1] =
                                     (*(volatile int *)&sh.exhausted != 0) &&
                                     (*(volatile int *)&sh.live == 0);
+#endif
                         named_barrier_sync(1, 32 * RS_STEP_WARPS);
                         if (*(volatile int *)&sh.stop[round & 1]) break;
 #else
@@ -1045,9 +1424,27 @@ cudaError_t launch_resident(const Physics & p, const Cfg & cfg, const Geo & geo,
         const long want = (n + per_cta - 1) / per_cta;
         int grid = (want < t.sms) ? (int)want : t.sms;
         if ((t.grid_cap > 0) && (t.grid_cap < grid)) grid = t.grid_cap;
+        /* Offload: one CTA in 15 serves the hard inelastic events of the
+         * others (headline workload on B200: 8 to 16 of 148 give the same
+         * throughput, 4 starve the stepping CTAs). */
+        int n_del_ctas = 0;
+        if (RS_OFFLOAD) {
+                n_del_ctas = (t.del_ctas > 0) ? t.del_ctas : (grid + 7) / 15;
+                if (n_del_ctas < 1) n_del_ctas = 1;
+                if (n_del_ctas > 16) n_del_ctas = 16;
+                if (grid + n_del_ctas > t.sms) grid = t.sms - n_del_ctas;
+                if (grid < 1) return cudaErrorInvalidConfiguration;
+        }
         unsigned long long * cursor =
             static_cast<unsigned long long *>(workspace);
-        e = cudaMemsetAsync(cursor, 0, sizeof(unsigned long long), stream);
+        if (RS_OFFLOAD) {
+                resident_offload_init<<<(RS_GENTRIES + 255) / 256, 256, 0,
+                    stream>>>(static_cast<unsigned char *>(workspace));
+                e = cudaGetLastError();
+        } else {
+                e = cudaMemsetAsync(
+                    cursor, 0, sizeof(unsigned long long), stream);
+        }
         if (e != cudaSuccess) return e;
         if (t.stats != nullptr)
                 cudaMemsetAsync(t.stats, 0, N_STATS * sizeof *t.stats, stream);
@@ -1062,10 +1459,13 @@ cudaError_t launch_resident(const Physics & p, const Cfg & cfg, const Geo & geo,
         a.n_random = n_random;
         a.n_steps = n_steps;
         a.cursor = cursor;
+        a.workspace = static_cast<unsigned char *>(workspace);
+        a.n_del_ctas = n_del_ctas;
         a.stats = t.stats;
         a.ehs_period = (t.ehs_period > 0) ? t.ehs_period : RS_EHS_PERIOD;
         a.del_threshold =
             (t.del_threshold > 0) ? t.del_threshold : RS_DEL_THRESHOLD;
+        grid += n_del_ctas;
         transport_resident_kernel<Cfg, Geo>
             <<<grid, RS_THREADS, smem, stream>>>(p, cfg, geo, a);
         e = cudaGetLastError();
