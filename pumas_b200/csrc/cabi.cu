@@ -1165,7 +1165,7 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
         c->last_ms = ms;
-        c->last_launches = 1;
+        c->last_launches = pb::transport_last_launches();
         c->last_n = n;
         c->track_offset += (unsigned long long)n;
 

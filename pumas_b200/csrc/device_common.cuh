@@ -153,6 +153,14 @@ inline const Tunables & tunables()
         return t;
 }
 
+/* Kernels launched by the last launch_transport of this process (diagnostics:
+ * pumas_b200_context_last_kernel_time). */
+inline int & last_launch_count()
+{
+        static int n = 0;
+        return n;
+}
+
 /* The workspace holds the global work cursor and, for the kernels that hand
  * the hard inelastic events over to dedicated CTAs (resident.cuh,
  * PB_RS_OFFLOAD), their queues and parking area. */

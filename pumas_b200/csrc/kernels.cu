@@ -52,6 +52,8 @@ PB_SPECIALISATION(launch_spec_straggled_noscat_forward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_backward);
 PB_SPECIALISATION(launch_spec_csda);
 
+int transport_last_launches() { return last_launch_count(); }
+
 cudaError_t transport_workspace_bytes(size_t * bytes)
 {
         *bytes = workspace_bytes();
@@ -65,6 +67,7 @@ cudaError_t launch_transport(const Physics & p, const Settings & cfg,
     int kernel, cudaStream_t stream)
 {
         if (n <= 0) return cudaSuccess;
+        last_launch_count() = 1;
         if (kernel == KERNEL_MONOLITHIC) {
                 const long blocks = (n + TRANSPORT_BLOCK - 1) / TRANSPORT_BLOCK;
                 transport_kernel<<<(unsigned int)blocks, TRANSPORT_BLOCK, 0,

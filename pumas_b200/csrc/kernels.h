@@ -27,6 +27,9 @@ enum {
 /* Size of the device scratch buffer launch_transport needs (work cursor and
  * the global work cursor). */
 cudaError_t transport_workspace_bytes(size_t * bytes);
+/* Kernels launched by the last launch_transport (1, or 2 when the queues of
+ * the DEL CTAs are prepared by resident_offload_init). */
+int transport_last_launches();
 
 /* Transport n tracks. All pointers are device pointers; `status` receives the
  * first non-zero pumas_return raised by a track, `workspace` is a scratch

@@ -816,7 +816,11 @@ __device__ __forceinline__ void courier_loop(const BatchArgs & a,
                         if (lane == 0) *(volatile int *)&sh.over = 1;
                         break;
                 }
-                if (!__any_sync(RS_FULL, moved)) __nanosleep(500);
+#ifndef PB_RS_COURIER_SLEEP
+#define PB_RS_COURIER_SLEEP 500
+#endif
+                if (!__any_sync(RS_FULL, moved))
+                        __nanosleep(PB_RS_COURIER_SLEEP);
                 still = __any_sync(RS_FULL, moved) ? 0 : still + 1;
                 if ((still > 0) && ((still & 0x1fffff) == 0)) {
                         /* watchdog, as in the DEL CTAs */
@@ -1466,6 +1470,7 @@ cudaError_t launch_resident(const Physics & p, const Cfg & cfg, const Geo & geo,
         a.del_threshold =
             (t.del_threshold > 0) ? t.del_threshold : RS_DEL_THRESHOLD;
         grid += n_del_ctas;
+        last_launch_count() = RS_OFFLOAD ? 2 : 1;
         transport_resident_kernel<Cfg, Geo>
             <<<grid, RS_THREADS, smem, stream>>>(p, cfg, geo, a);
         e = cudaGetLastError();
