@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=4)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--tracks", type=int, default=1 << 21,
+    ap.add_argument("--tracks", type=int, default=1 << 23,
                     help="tracks per step and per GPU")
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="tracks of the CPU baseline sample (0: auto)")

@@ -25,6 +25,11 @@ namespace {
 constexpr int TALLY_THREADS = 256;
 constexpr int TALLY_BLOCKS = 592;
 
+constexpr int TALLY_SHARED_BINS = 2048;
+
+/* Counts are integers (any order gives the same totals): a thread counts in
+ * registers, a CTA in shared memory (histogram of up to TALLY_SHARED_BINS
+ * bins), and only the CTA totals go to the global counters. */
 __global__ void __launch_bounds__(TALLY_THREADS)
     tally_kernel(const pb::State * __restrict__ states,
         const int * __restrict__ events, long n, int event_mask,
@@ -33,15 +38,25 @@ __global__ void __launch_bounds__(TALLY_THREADS)
         unsigned long long * __restrict__ counts /* [2 + n_bins] */)
 {
         __shared__ double s_w[TALLY_THREADS], s_w2[TALLY_THREADS];
+        __shared__ unsigned int s_hist[TALLY_SHARED_BINS];
+        __shared__ unsigned long long s_n[2];
+        const bool shared_hist = (n_bins <= TALLY_SHARED_BINS);
+        if (shared_hist)
+                for (int b = threadIdx.x; b < n_bins; b += TALLY_THREADS)
+                        s_hist[b] = 0u;
+        if (threadIdx.x < 2) s_n[threadIdx.x] = 0ull;
+        __syncthreads();
+
         double w = 0., w2 = 0.;
+        unsigned long long n_all = 0ull, n_selected = 0ull;
         const long stride = (long)gridDim.x * blockDim.x;
         for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
              i += stride) {
                 const int e = (events != nullptr) ? events[i] : 0;
                 const bool selected = (event_mask == 0) || (e & event_mask);
-                atomicAdd(&counts[0], 1ull);
+                n_all++;
                 if (!selected) continue;
-                atomicAdd(&counts[1], 1ull);
+                n_selected++;
                 const double wi = states[i].weight;
                 w += wi;
                 w2 += wi * wi;
@@ -50,12 +65,18 @@ __global__ void __launch_bounds__(TALLY_THREADS)
                         const double x =
                             (log(k) - ln_emin) / (ln_emax - ln_emin);
                         int b = (int)floor(x * n_bins);
-                        if ((b >= 0) && (b < n_bins))
-                                atomicAdd(&counts[2 + b], 1ull);
+                        if ((b >= 0) && (b < n_bins)) {
+                                if (shared_hist)
+                                        atomicAdd(&s_hist[b], 1u);
+                                else
+                                        atomicAdd(&counts[2 + b], 1ull);
+                        }
                 }
         }
         s_w[threadIdx.x] = w;
         s_w2[threadIdx.x] = w2;
+        atomicAdd(&s_n[0], n_all);
+        atomicAdd(&s_n[1], n_selected);
         __syncthreads();
         for (int k = TALLY_THREADS / 2; k > 0; k >>= 1) {
                 if (threadIdx.x < k) {
@@ -68,6 +89,13 @@ __global__ void __launch_bounds__(TALLY_THREADS)
                 partial[2 * blockIdx.x] = s_w[0];
                 partial[2 * blockIdx.x + 1] = s_w2[0];
         }
+        if ((threadIdx.x < 2) && (s_n[threadIdx.x] != 0ull))
+                atomicAdd(&counts[threadIdx.x], s_n[threadIdx.x]);
+        if (shared_hist)
+                for (int b = threadIdx.x; b < n_bins; b += TALLY_THREADS)
+                        if (s_hist[b] != 0u)
+                                atomicAdd(&counts[2 + b],
+                                    (unsigned long long)s_hist[b]);
 }
 
 __global__ void tally_finish_kernel(const double * __restrict__ partial,
