@@ -7,7 +7,9 @@
  * dozen PCHIP look-ups, no loop, no random number. Nothing needs scheduling, so
  * the kernel is one thread per track; instantiated on (StaticSettings,
  * UniformGeometry) the stepping engine is unreachable and compiled out, which
- * leaves a small kernel (80 registers instead of 255, 24 warps per SM). Per
+ * leaves a small kernel (64 registers instead of 255, 32 warps per SM; the
+ * long scoreboard is its first stall, so occupancy is worth 24-48 B of spills:
+ * +2 to +11 % against 80 registers and 24 warps, profiles/r1_experiments.md). Per
  * track it moves 104 B of state in, 104 B out, 4 B of event (+ 16 B of optional
  * media and counters): 2.6 TB/s at 1.1e10 tracks/s, 40 % of the measured HBM
  * peak, and about as much time goes to issuing the ~6 table searches of a
@@ -21,9 +23,12 @@
 namespace pb {
 
 constexpr int CSDA_BLOCK = 256;
+#ifndef PB_CSDA_MIN_CTAS
+#define PB_CSDA_MIN_CTAS 4
+#endif
 
 template <class Cfg>
-__global__ void __launch_bounds__(CSDA_BLOCK)
+__global__ void __launch_bounds__(CSDA_BLOCK, PB_CSDA_MIN_CTAS)
     transport_csda_kernel(const Physics p, const Cfg cfg,
         const UniformGeometry geo, const BatchArgs a)
 {
