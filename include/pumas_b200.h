@@ -344,6 +344,48 @@ PUMAS_API enum pumas_return pumas_physics_table_index(
     enum pumas_mode mode, int material, double value, int * index);
 
 /* ------------------------------------------------------------------------
+ * Differential cross-section models (pumas.h:717, 2110-2284), host side.
+ * The models the device code implements (pb_dcs.h, pb_dcs_models.h) are
+ * exposed with the reference's signature: atomic DCS in m^2 / GeV for a target
+ * (Z, A), a projectile of mass m and kinetic energy K [GeV], energy loss q.
+ * ------------------------------------------------------------------------ */
+/* pumas.h:717 */
+typedef double pumas_dcs_t(double Z, double A, double m, double K, double q);
+
+/* pumas.c:13673-13699: the model (name, function) a physics was built with. */
+PUMAS_API enum pumas_return pumas_physics_dcs(
+    const struct pumas_physics * physics, enum pumas_process process,
+    const char ** model, pumas_dcs_t ** dcs);
+
+/* pumas.c:15469-15505: look up a model by name (NULL: the default one) among
+ * the built-in ones (bremsstrahlung ABB, KKP, SSR; pair production KKP, SSR;
+ * photonuclear BBKS, BM, DRSS). */
+PUMAS_API enum pumas_return pumas_dcs_get(
+    enum pumas_process process, const char * model, pumas_dcs_t ** dcs);
+
+/* pumas.c:15422-15466. Not supported: a host function cannot be evaluated by
+ * the transport kernels; returns PUMAS_RETURN_MODEL_ERROR. */
+PUMAS_API enum pumas_return pumas_dcs_register(
+    enum pumas_process process, const char * model, pumas_dcs_t * dcs);
+
+/* pumas.c:15532-15542 ("SSR", "SSR", "DRSS"); NULL for a bad process. */
+PUMAS_API const char * pumas_dcs_default(enum pumas_process process);
+
+/* pumas.c:15508-15529: kinematic range of the energy loss. */
+PUMAS_API enum pumas_return pumas_dcs_range(enum pumas_process process,
+    double Z, double mass, double energy, double * min, double * max);
+
+/* pumas.c:15545-15581: elastic (Coulomb) DCS of the hard scattering sampled
+ * by the transport (screened nucleus, spin and nuclear form factors), in
+ * m^2 / rad, at the laboratory angle theta. */
+PUMAS_API double pumas_elastic_dcs(
+    double Z, double A, double m, double K, double theta);
+
+/* pumas.c:11082-11101: close collisions with atomic electrons. */
+PUMAS_API double pumas_electronic_dcs(
+    double Z, double I, double m, double K, double q);
+
+/* ------------------------------------------------------------------------
  * Context (pumas.h:1214-1340)
  * ------------------------------------------------------------------------ */
 /* pumas.c:2545. Same defaults (pumas.c:2592-2605). */

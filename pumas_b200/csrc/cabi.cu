@@ -19,6 +19,9 @@
 #include <vector>
 
 #include "kernels.h"
+#include "pb_coulomb.h"
+#include "pb_dcs.h"
+#include "pb_dcs_models.h"
 #include "pb_dump.hpp"
 #include "pb_tables.h"
 #include "pumas_b200.h"
@@ -348,6 +351,10 @@ const char * pumas_error_function(pumas_function_t * caller)
         NAME(pumas_b200_context_last_kernel_time)
         NAME(pumas_error_raise)
         NAME(pumas_constant)
+        NAME(pumas_physics_dcs)
+        NAME(pumas_dcs_get)
+        NAME(pumas_dcs_register)
+        NAME(pumas_dcs_range)
 #undef NAME
         return nullptr;
 }
@@ -1230,6 +1237,198 @@ enum pumas_return pumas_b200_context_last_kernel_time(
         if (milliseconds != nullptr) *milliseconds = c->last_ms;
         if (launches != nullptr) *launches = c->last_launches;
         return PUMAS_RETURN_SUCCESS;
+}
+
+} /* extern "C" */
+
+/* ---- DCS models on the host: pumas.c:13673-13699, 15376-15543 ---------------
+ * The functions below evaluate the very code the kernels run (pb_dcs.h,
+ * pb_dcs_models.h are single-source host/device), behind the reference's
+ * pumas_dcs_t signature. */
+namespace {
+
+const pb::Physics & model_constants()
+{
+        static pb::Physics constants;
+        static std::once_flag once;
+        std::call_once(once, [] {
+                std::memset(&constants, 0, sizeof constants);
+                /* as load_physics_bytes (pb_dump.hpp): run time libm */
+                volatile double one = 1., half = 0.5, m16 = -1. / 6.,
+                                t13 = 1. / 3., m13 = -1. / 3.;
+                constants.c_exp_1 = exp(one);
+                constants.c_exp_1_2 = exp(half);
+                constants.c_exp_m1_6 = exp(m16);
+                constants.c_exp_1_3 = exp(t13);
+                constants.c_exp_m1_3 = exp(m13);
+        });
+        return constants;
+}
+
+#define MODEL_WITH_CONSTANTS(name)                                             \
+        double api_##name(double Z, double A, double m, double K, double q)    \
+        {                                                                      \
+                pb::Element el;                                                \
+                pb::detail::element_fill(el, Z, A, 0.);                        \
+                return pb::name(model_constants(), el, m, K, q);               \
+        }
+#define MODEL(name)                                                            \
+        double api_##name(double Z, double A, double m, double K, double q)    \
+        {                                                                      \
+                pb::Element el;                                                \
+                pb::detail::element_fill(el, Z, A, 0.);                        \
+                return pb::name(el, m, K, q);                                  \
+        }
+MODEL_WITH_CONSTANTS(dcs_bremsstrahlung_SSR)
+MODEL(dcs_bremsstrahlung_KKP)
+MODEL(dcs_bremsstrahlung_ABB)
+MODEL_WITH_CONSTANTS(dcs_pair_production_SSR)
+MODEL(dcs_pair_production_KKP)
+MODEL(dcs_photonuclear_DRSS)
+MODEL(dcs_photonuclear_BM)
+MODEL(dcs_photonuclear_BBKS)
+#undef MODEL
+#undef MODEL_WITH_CONSTANTS
+
+/* Indexed like pb::Physics::model (pb_dump.hpp, `known`). */
+struct ModelEntry {
+        const char * name;
+        pumas_dcs_t * dcs;
+};
+const ModelEntry MODELS[3][3] = {
+        { { "SSR", &api_dcs_bremsstrahlung_SSR },
+            { "KKP", &api_dcs_bremsstrahlung_KKP },
+            { "ABB", &api_dcs_bremsstrahlung_ABB } },
+        { { "SSR", &api_dcs_pair_production_SSR },
+            { "KKP", &api_dcs_pair_production_KKP }, { nullptr, nullptr } },
+        { { "DRSS", &api_dcs_photonuclear_DRSS },
+            { "BM", &api_dcs_photonuclear_BM },
+            { "BBKS", &api_dcs_photonuclear_BBKS } }
+};
+const char * const PROCESS_NAME[3] = { "bremsstrahlung", "pair production",
+        "photonuclear" };
+
+} /* namespace */
+
+extern "C" {
+
+enum pumas_return pumas_physics_dcs(const struct pumas_physics * physics,
+    enum pumas_process process, const char ** model, pumas_dcs_t ** dcs)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_dcs, PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        if (((int)process < 0) || (process > PUMAS_PROCESS_PHOTONUCLEAR))
+                return RAISE(pumas_physics_dcs, PUMAS_RETURN_INDEX_ERROR,
+                    "bad process (expected a value in [0, 2], got %u)",
+                    (unsigned int)process);
+        const ModelEntry & entry =
+            MODELS[process][physics->host.view.model[process]];
+        if (dcs != nullptr) *dcs = entry.dcs;
+        if (model != nullptr) *model = entry.name;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_dcs_get(
+    enum pumas_process process, const char * model, pumas_dcs_t ** dcs)
+{
+        if (((int)process < 0) || (process > PUMAS_PROCESS_PHOTONUCLEAR))
+                return RAISE(pumas_dcs_get, PUMAS_RETURN_INDEX_ERROR,
+                    "bad process (expected an index in [0, %d], got %u)",
+                    (int)PUMAS_PROCESS_PHOTONUCLEAR, (unsigned int)process);
+        if (model == nullptr) model = MODELS[process][0].name;
+        for (int k = 0; k < 3; k++) {
+                const ModelEntry & entry = MODELS[process][k];
+                if ((entry.name != nullptr) &&
+                    (strcmp(entry.name, model) == 0)) {
+                        *dcs = entry.dcs;
+                        return PUMAS_RETURN_SUCCESS;
+                }
+        }
+        *dcs = nullptr;
+        return RAISE(pumas_dcs_get, PUMAS_RETURN_MODEL_ERROR,
+            "model %s not found for %s process", model, PROCESS_NAME[process]);
+}
+
+enum pumas_return pumas_dcs_register(
+    enum pumas_process process, const char * model, pumas_dcs_t * dcs)
+{
+        (void)process;
+        (void)dcs;
+        return RAISE(pumas_dcs_register, PUMAS_RETURN_MODEL_ERROR,
+            "cannot register model %s: a host function cannot be evaluated "
+            "by the transport kernels", (model != nullptr) ? model : "(null)");
+}
+
+const char * pumas_dcs_default(enum pumas_process process)
+{
+        if (((int)process < 0) || (process > PUMAS_PROCESS_PHOTONUCLEAR))
+                return nullptr;
+        return MODELS[process][0].name;
+}
+
+enum pumas_return pumas_dcs_range(enum pumas_process process, double Z,
+    double mass, double energy, double * min, double * max)
+{
+        if (((int)process < 0) || (process > PUMAS_PROCESS_PHOTONUCLEAR))
+                return RAISE(pumas_dcs_range, PUMAS_RETURN_INDEX_ERROR,
+                    "bad process (expected an index in [0, %d], got %u)",
+                    (int)PUMAS_PROCESS_PHOTONUCLEAR, (unsigned int)process);
+        double qmin, qmax;
+        if (process == PUMAS_PROCESS_PHOTONUCLEAR) {
+                pb::dcs_photonuclear_range(mass, energy, &qmin, &qmax);
+        } else {
+                pb::Element el;
+                pb::detail::element_fill(el, Z, 1., 0.);
+                pb::dcs_pair_production_range(el, mass, energy, &qmin, &qmax);
+                if (process == PUMAS_PROCESS_BREMSSTRAHLUNG) qmin = 0.;
+        }
+        if (min != nullptr) *min = qmin;
+        if (max != nullptr) *max = qmax;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* pumas.c:15545-15581, on the Coulomb functions of the kernels (pb_coulomb.h). */
+double pumas_elastic_dcs(double Z, double A, double m, double K, double theta)
+{
+        if ((Z < 1.) || (A < 1.) || (m <= 0.) || (K <= 0.)) return 0.;
+
+        pb::Element el;
+        pb::detail::element_fill(el, Z, A, 0.);
+        int n_parameters;
+        double kinetic0, amplitude[3], screening[pb::MAX_SCREENING + 1];
+        double fCM[2];
+        pb::coulomb_frame_parameters(Z, A, m, K, &kinetic0, fCM);
+        pb::coulomb_screening_parameters(
+            el, m, K, kinetic0, &n_parameters, amplitude, screening);
+        const double fspin = pb::coulomb_spin_factor(m, K);
+
+        const double c = cos(theta);
+        const double s = sin(theta);
+        const double gs = fCM[0] * s;
+        const double sd = sqrt(c * c + gs * gs * (1. - fCM[1] * fCM[1]));
+        const double cgs = c * c + gs * gs;
+        const double mu0 =
+            0.5 * (gs * gs * (1. + fCM[1]) + c * (c - sd)) / cgs;
+        const double num = fCM[0] * (c * fCM[1] + sd);
+        const double jac = num * num / (cgs * cgs * sd);
+
+        const int n = n_parameters - 1;
+        double dcs = 0.;
+        for (int i = 0; i < n; i++) dcs += amplitude[i] / (screening[i] + mu0);
+        dcs *= pb::coulomb_nuclear_form_factor(mu0, screening[n]);
+        dcs *= dcs;
+
+        const double p0 = sqrt(kinetic0 * (kinetic0 + 2. * m));
+        const double p = sqrt(K * (K + 2. * m));
+        const double factor =
+            0.5 * pb::ALPHA_EM * Z * (K + m) * pb::HBAR_C / (p0 * p);
+        return factor * factor * dcs * jac * (1. - fspin * mu0);
+}
+
+double pumas_electronic_dcs(double Z, double I, double m, double K, double q)
+{
+        return pb::electronic_dcs(Z, I, m, K, q);
 }
 
 } /* extern "C" */
