@@ -381,6 +381,12 @@ PUMAS_API enum pumas_return pumas_dcs_range(enum pumas_process process,
 PUMAS_API double pumas_elastic_dcs(
     double Z, double A, double m, double K, double theta);
 
+/* pumas.c:15584-15609: elastic path length (order 0) or first transport path
+ * length (order 1), in kg/m^2, for a target (Z, A). Evaluated on the host in
+ * `long double` like the reference. */
+PUMAS_API double pumas_elastic_path(
+    int order, double Z, double A, double mass, double kinetic);
+
 /* pumas.c:11082-11101: close collisions with atomic electrons. */
 PUMAS_API double pumas_electronic_dcs(
     double Z, double I, double m, double K, double q);

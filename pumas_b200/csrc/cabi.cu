@@ -1426,6 +1426,77 @@ double pumas_elastic_dcs(double Z, double A, double m, double K, double theta)
         return factor * factor * dcs * jac * (1. - fspin * mu0);
 }
 
+/* pumas.c:15584-15609. Host only: the pole reduction and the transport
+ * coefficients run in `long double`, as in the reference (the kernels use the
+ * double-double instantiation of the same templates, pb_coulomb.h). */
+#pragma nv_diag_suppress 20208
+double pumas_elastic_path(
+    int order, double Z, double A, double mass, double kinetic)
+{
+        if ((order < 0) || (order > 1) || (kinetic <= 0.)) return 0.;
+
+        typedef long double real;
+        pb::Element el;
+        pb::detail::element_fill(el, Z, A, 0.);
+        int n_parameters;
+        double kinetic0, amplitude[3], screening[pb::MAX_SCREENING + 1];
+        double fCM[2];
+        pb::coulomb_frame_parameters(Z, A, mass, kinetic, &kinetic0, fCM);
+        pb::coulomb_screening_parameters(
+            el, mass, kinetic, kinetic0, &n_parameters, amplitude, screening);
+        const double fspin = pb::coulomb_spin_factor(mass, kinetic);
+        pb::CoulombPoles<real> poles;
+        pb::coulomb_pole_reduction(n_parameters, amplitude, screening, &poles);
+
+        double coefficient;
+        if (order == 0) {
+                coefficient = pb::coulomb_transport_cs0(
+                    1., fspin, n_parameters, screening, poles);
+        } else {
+                /* Order 1 coefficient over the whole angular range (mu = 1),
+                 * pumas.c:7623-7683: per pole, the moments of 1 / (x + mu) and
+                 * 1 / (x + mu)^2 weighted by mu (1 - S mu); the nuclear term
+                 * adds the poles of order 3 and 4. The accumulator is binary64
+                 * (each term is rounded when added). */
+                const real S = fspin, mu = 1.;
+                const int n = n_parameters - 1;
+                double cs1 = 0.;
+                real x, r, L, I0, I1, J1, I2, J2;
+                auto moments = [&](double pole) {
+                        x = pole;
+                        r = mu / (mu + x);
+                        L = logl(1. + mu / x);
+                        I0 = r / x;
+                        I1 = L - r;
+                        J1 = -x * L;
+                        I2 = mu + x * (r - 2. * L);
+                        J2 = x * (x * L - mu);
+                };
+                for (int i = 0; i < n; i++) {
+                        moments(screening[i]);
+                        cs1 += poles.a[i] * (J1 - S * J2) +
+                            poles.b[i] * (I1 - S * I2);
+                }
+                moments(screening[n]);
+                const real rn = 1. / (1. + mu / x);
+                const real K0 = (1. - rn) * (1. + rn) / (2 * x * x);
+                const real L0 = (1. - rn) * ((1. + rn) * (1. + rn) - rn) /
+                    (3 * x * x * x);
+                const real K1 = I0 - x * K0;
+                const real L1 = K0 - x * L0;
+                const real K2 = I1 - x * K1;
+                const real L2 = K1 - x * L1;
+                cs1 += poles.c[0] * (J1 - S * J2) + poles.c[1] * (I1 - S * I2) +
+                    poles.c[2] * (K1 - S * K2) + poles.c[3] * (L1 - S * L2);
+                const double d = 1. / (fCM[0] * (1. + fCM[1]));
+                coefficient = 2 * cs1;
+                coefficient *= d * d;
+        }
+        return pb::coulomb_normalisation(Z, A, mass, kinetic, kinetic0) /
+            coefficient;
+}
+#pragma nv_diag_default 20208
+
 double pumas_electronic_dcs(double Z, double I, double m, double K, double q)
 {
         return pb::electronic_dcs(Z, I, m, K, q);

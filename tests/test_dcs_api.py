@@ -36,6 +36,8 @@ def _prototype(lib):
     lib.pumas_electronic_dcs.argtypes = [ctypes.c_double] * 5
     lib.pumas_elastic_dcs.restype = ctypes.c_double
     lib.pumas_elastic_dcs.argtypes = [ctypes.c_double] * 5
+    lib.pumas_elastic_path.restype = ctypes.c_double
+    lib.pumas_elastic_path.argtypes = [ctypes.c_int] + [ctypes.c_double] * 4
     return lib
 
 
@@ -113,6 +115,17 @@ def test_elastic_dcs_bit_exact(libs):
                 # (both NaN beyond the kinematic limit of a light target)
                 assert (a == b) or (a != a and b != b), (
                     Z, A, m, k, theta, a, b)
+    # pumas_elastic_path (pumas.c:15584): pole reduction and transport
+    # coefficients in long double on the host, as the reference
+    for Z, A in TARGETS:
+        for m in MASSES:
+            for k in np.exp(rng.uniform(np.log(1e-4), np.log(1e7), 100)):
+                for order in (0, 1):
+                    a = ref.pumas_elastic_path(order, Z, A, m, float(k))
+                    b = ours.pumas_elastic_path(order, Z, A, m, float(k))
+                    assert (a == b) or (a != a and b != b), (
+                        order, Z, A, m, k, a, b)
+    assert ours.pumas_elastic_path(2, 11., 22., 0.1, 1.) == 0.
     assert ours.pumas_elastic_dcs(0.5, 1., 0.1, 1., 0.1) == 0.
     assert ours.pumas_elastic_dcs(1., 1., 0.1, 0., 0.1) == 0.
 
