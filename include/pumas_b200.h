@@ -474,6 +474,16 @@ PUMAS_API void pumas_error_handler_set(pumas_handler_cb * handler);
 PUMAS_API pumas_handler_cb * pumas_error_handler_get(void);
 PUMAS_API void pumas_error_catch(int enable);
 PUMAS_API enum pumas_return pumas_error_raise(void);
+/* pumas.h:2020-2079: user supplied allocation of the host objects the library
+ * hands out (physics, contexts and their user_data). NULL restores malloc /
+ * realloc / free. Not thread safe, like the reference. */
+typedef void * pumas_allocate_cb(size_t size);
+typedef void * pumas_reallocate_cb(void * ptr, size_t size);
+typedef void pumas_deallocate_cb(void * ptr);
+PUMAS_API void pumas_memory_allocator(pumas_allocate_cb * allocator);
+PUMAS_API void pumas_memory_reallocator(pumas_reallocate_cb * reallocator);
+PUMAS_API void pumas_memory_deallocator(pumas_deallocate_cb * deallocator);
+
 PUMAS_API void pumas_version(int * major, int * minor, int * patch);
 PUMAS_API enum pumas_return pumas_constant(
     enum pumas_constant index, double * value);

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -68,6 +69,14 @@ struct ContextImpl {
         /* user memory follows */
         double data[1];
 };
+
+/* ---- host memory hooks, pumas.c:1368-1398 -----------------------------------
+ * The library objects handed to the user (struct pumas_physics, struct
+ * pumas_context and its user_data) are allocated with these; the C++
+ * containers inside a physics object and the device memory are not. */
+pumas_allocate_cb * g_allocate = &malloc;
+pumas_reallocate_cb * g_reallocate = &realloc;
+pumas_deallocate_cb * g_deallocate = &free;
 
 /* ---- error machinery, pumas.c:203-270, 2299-2327, 7814-7859 --------------- */
 void default_handler(
@@ -359,6 +368,22 @@ const char * pumas_error_function(pumas_function_t * caller)
         return nullptr;
 }
 
+/* pumas.c:1379-1398: NULL restores the C library function. */
+void pumas_memory_allocator(pumas_allocate_cb * allocator)
+{
+        g_allocate = (allocator == nullptr) ? &malloc : allocator;
+}
+
+void pumas_memory_reallocator(pumas_reallocate_cb * reallocator)
+{
+        g_reallocate = (reallocator == nullptr) ? &realloc : reallocator;
+}
+
+void pumas_memory_deallocator(pumas_deallocate_cb * deallocator)
+{
+        g_deallocate = (deallocator == nullptr) ? &free : deallocator;
+}
+
 void pumas_version(int * major, int * minor, int * patch)
 {
         if (major != nullptr) *major = PUMAS_VERSION_MAJOR;
@@ -387,6 +412,16 @@ enum pumas_return pumas_constant(enum pumas_constant index, double * value)
 int pumas_b200_device_available(void) { return device_usable(nullptr); }
 
 /* ---- physics --------------------------------------------------------------- */
+} /* extern "C" */
+namespace {
+void physics_delete(pumas_physics * physics)
+{
+        physics->~pumas_physics();
+        g_deallocate(physics);
+}
+} /* namespace */
+extern "C" {
+
 enum pumas_return pumas_physics_load(
     struct pumas_physics ** physics_ptr, FILE * stream)
 {
@@ -397,7 +432,9 @@ enum pumas_return pumas_physics_load(
         if (stream == nullptr)
                 return RAISE(pumas_physics_load, PUMAS_RETURN_PATH_ERROR,
                     "invalid input stream (null)");
-        pumas_physics * physics = new (std::nothrow) pumas_physics;
+        void * const memory = g_allocate(sizeof(pumas_physics));
+        pumas_physics * physics =
+            (memory != nullptr) ? new (memory) pumas_physics : nullptr;
         if (physics == nullptr)
                 return RAISE(pumas_physics_load, PUMAS_RETURN_MEMORY_ERROR,
                     "could not allocate memory");
@@ -406,12 +443,12 @@ enum pumas_return pumas_physics_load(
         std::string err;
         const int rc = pb::load_physics_stream(stream, physics->host, err);
         if (rc != 0) {
-                delete physics;
+                physics_delete(physics);
                 return RAISE(pumas_physics_load, (enum pumas_return)rc, "%s",
                     err.c_str());
         }
         if (physics->host.view.max_components > pb::MAX_COMPONENTS) {
-                delete physics;
+                physics_delete(physics);
                 return RAISE(pumas_physics_load, PUMAS_RETURN_MEMORY_ERROR,
                     "materials with more than %d elements are not supported",
                     pb::MAX_COMPONENTS);
@@ -456,7 +493,7 @@ void pumas_physics_destroy(struct pumas_physics ** physics_ptr)
         if ((physics_ptr == nullptr) || (*physics_ptr == nullptr)) return;
         pumas_physics * physics = *physics_ptr;
         if (physics->d_image != nullptr) cudaFree(physics->d_image);
-        delete physics;
+        physics_delete(physics);
         *physics_ptr = nullptr;
 }
 
@@ -884,11 +921,12 @@ enum pumas_return pumas_context_create(struct pumas_context ** context_,
                 return RAISE(pumas_context_create, PUMAS_RETURN_PHYSICS_ERROR,
                     "the Physics has not been initialised");
         if (extra_memory < 0) extra_memory = 0;
-        ContextImpl * c = static_cast<ContextImpl *>(
-            calloc(1, sizeof(ContextImpl) + (size_t)extra_memory + 16));
+        const size_t size = sizeof(ContextImpl) + (size_t)extra_memory + 16;
+        ContextImpl * c = static_cast<ContextImpl *>(g_allocate(size));
         if (c == nullptr)
                 return RAISE(pumas_context_create, PUMAS_RETURN_MEMORY_ERROR,
                     "could not allocate memory");
+        memset(c, 0x0, size);
         c->physics = physics;
         c->extra_memory = extra_memory;
         c->api.user_data = (extra_memory > 0) ? c->data : nullptr;
@@ -920,7 +958,7 @@ void pumas_context_destroy(struct pumas_context ** context)
                 cudaEventDestroy(c->ev0);
                 cudaEventDestroy(c->ev1);
         }
-        free(c);
+        g_deallocate(c);
         *context = nullptr;
 }
 

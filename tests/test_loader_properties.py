@@ -115,3 +115,58 @@ def test_error_catch_and_raise(physics):
     assert rc2 == 0
     assert lib.pumas_error_raise() == 22  # first caught error is re-raised
     assert lib.pumas_error_raise() == 18  # RAISE_ERROR: nothing was caught
+
+
+def test_memory_hooks(physics):
+    """pumas_memory_allocator / _deallocator (pumas.c:1379-1398): the objects
+    handed to the user go through the hooks; NULL restores malloc / free."""
+    import ctypes
+    lib = pb.library()
+    libc = ctypes.CDLL(None)
+    libc.malloc.restype = ctypes.c_void_p
+    libc.malloc.argtypes = [ctypes.c_size_t]
+    libc.free.argtypes = [ctypes.c_void_p]
+    calls = {"malloc": [], "free": []}
+
+    @ctypes.CFUNCTYPE(ctypes.c_void_p, ctypes.c_size_t)
+    def allocate(size):
+        p = libc.malloc(size)
+        calls["malloc"].append((p, size))
+        return p
+
+    @ctypes.CFUNCTYPE(None, ctypes.c_void_p)
+    def deallocate(p):
+        calls["free"].append(p)
+        libc.free(p)
+
+    lib.pumas_memory_allocator.argtypes = [ctypes.c_void_p]
+    lib.pumas_memory_deallocator.argtypes = [ctypes.c_void_p]
+    lib.pumas_memory_reallocator.argtypes = [ctypes.c_void_p]
+    lib.pumas_memory_allocator(ctypes.cast(allocate, ctypes.c_void_p))
+    lib.pumas_memory_deallocator(ctypes.cast(deallocate, ctypes.c_void_p))
+    try:
+        ctx = ctypes.POINTER(pb.ContextStruct)()
+        assert lib.pumas_context_create(
+            ctypes.byref(ctx), physics._handle, 64) == 0
+        assert len(calls["malloc"]) == 1 and calls["malloc"][0][1] > 64
+        base, size = calls["malloc"][0]
+        user = ctypes.cast(ctx.contents.user_data, ctypes.c_void_p).value
+        assert base < user and user + 64 <= base + size
+        assert ctx.contents.accuracy == 1e-2  # zeroed, then the defaults
+        lib.pumas_context_destroy(ctypes.byref(ctx))
+        assert calls["free"] == [base] and not ctx
+
+        other = pb.Physics(harness.dump_path())
+        assert len(calls["malloc"]) == 2
+        handle = other._handle.value
+        assert handle == calls["malloc"][1][0]
+        del other
+        assert calls["free"][-1] == handle
+    finally:
+        lib.pumas_memory_allocator(None)
+        lib.pumas_memory_deallocator(None)
+        lib.pumas_memory_reallocator(None)
+    n = len(calls["malloc"])
+    ctx = pb.Context(physics)
+    del ctx
+    assert len(calls["malloc"]) == n
