@@ -409,6 +409,15 @@ PUMAS_API enum pumas_return pumas_context_random_seed_set(
 PUMAS_API enum pumas_return pumas_context_random_seed_get(
     struct pumas_context * context, unsigned long * seed);
 
+/* pumas.c:2415-2492. The random state of a context is (seed, id of its next
+ * first track): the streams are counter based, so that is all a later run
+ * needs to resume with the same variates. The format differs from the
+ * reference's (a Mersenne Twister state). */
+PUMAS_API enum pumas_return pumas_context_random_dump(
+    struct pumas_context * context, FILE * stream);
+PUMAS_API enum pumas_return pumas_context_random_load(
+    struct pumas_context * context, FILE * stream);
+
 /* New. Attach a built-in geometry (copied) to the context; replaces setting
  * `context->medium` (pumas.h:641). */
 PUMAS_API enum pumas_return pumas_b200_context_geometry_set(

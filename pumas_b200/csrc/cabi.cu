@@ -350,6 +350,8 @@ const char * pumas_error_function(pumas_function_t * caller)
         NAME(pumas_context_create)
         NAME(pumas_context_random_seed_set)
         NAME(pumas_context_random_seed_get)
+        NAME(pumas_context_random_dump)
+        NAME(pumas_context_random_load)
         NAME(pumas_context_transport)
         NAME(pumas_context_transport_n)
         NAME(pumas_b200_context_geometry_set)
@@ -1051,6 +1053,66 @@ enum pumas_return pumas_b200_context_geometry_set(
         }
         c->geometry = *geometry;
         c->has_geometry = 1;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* pumas.c:2415-2492. The state of the random streams of a context is its seed
+ * and the id of its next first track (Philox is counter based): a tag, then
+ * the two 64 bit words. */
+static const int RANDOM_DUMP_TAG = 0xB200;
+
+enum pumas_return pumas_context_random_dump(
+    struct pumas_context * context, FILE * stream)
+{
+        if (context == nullptr)
+                return RAISE(pumas_context_random_dump,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        if (stream == nullptr)
+                return RAISE(pumas_context_random_dump,
+                    PUMAS_RETURN_PATH_ERROR, "invalid input stream (null)");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        if (!c->seed_set) {
+                /* pumas.c:2432-2438: initialise the stream first */
+                const enum pumas_return rc =
+                    pumas_context_random_seed_set(context, nullptr);
+                if (rc != PUMAS_RETURN_SUCCESS) return rc;
+        }
+        const unsigned long long words[2] = {
+                (unsigned long long)c->seed,
+                (unsigned long long)c->track_offset };
+        if ((fwrite(&RANDOM_DUMP_TAG, sizeof RANDOM_DUMP_TAG, 1, stream) !=
+                1) ||
+            (fwrite(words, sizeof words, 1, stream) != 1))
+                return RAISE(pumas_context_random_dump, PUMAS_RETURN_IO_ERROR,
+                    "could not not write to stream");
+        return PUMAS_RETURN_SUCCESS;
+}
+
+enum pumas_return pumas_context_random_load(
+    struct pumas_context * context, FILE * stream)
+{
+        if (context == nullptr)
+                return RAISE(pumas_context_random_load,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        if (stream == nullptr)
+                return RAISE(pumas_context_random_load,
+                    PUMAS_RETURN_PATH_ERROR, "invalid input stream (null)");
+        int tag;
+        unsigned long long words[2];
+        if (fread(&tag, sizeof tag, 1, stream) != 1)
+                return RAISE(pumas_context_random_load, PUMAS_RETURN_IO_ERROR,
+                    "could not read from stream");
+        if (tag != RANDOM_DUMP_TAG)
+                return RAISE(pumas_context_random_load,
+                    PUMAS_RETURN_FORMAT_ERROR,
+                    "incompatible version of binary dump");
+        if (fread(words, sizeof words, 1, stream) != 1)
+                return RAISE(pumas_context_random_load, PUMAS_RETURN_IO_ERROR,
+                    "could not read from stream");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        c->seed = (unsigned long)words[0];
+        c->seed_set = 1;
+        c->track_offset = words[1];
         return PUMAS_RETURN_SUCCESS;
 }
 

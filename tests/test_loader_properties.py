@@ -170,3 +170,51 @@ def test_memory_hooks(physics):
     ctx = pb.Context(physics)
     del ctx
     assert len(calls["malloc"]) == n
+
+
+def test_random_dump_and_load(physics, tmp_path):
+    """pumas_context_random_dump / _load (pumas.c:2415-2492): the state of the
+    counter based streams is (seed, id of the next first track)."""
+    import ctypes
+    lib = pb.library()
+    libc = ctypes.CDLL(None)
+    libc.fopen.restype = ctypes.c_void_p
+    libc.fopen.argtypes = [ctypes.c_char_p, ctypes.c_char_p]
+    libc.fclose.argtypes = [ctypes.c_void_p]
+    for f in (lib.pumas_context_random_dump, lib.pumas_context_random_load):
+        f.argtypes = [ctypes.POINTER(pb.ContextStruct), ctypes.c_void_p]
+    lib.pumas_context_random_seed_get.argtypes = [
+        ctypes.POINTER(pb.ContextStruct), ctypes.POINTER(ctypes.c_ulong)]
+
+    a = pb.Context(physics, seed=123456789)
+    a.track_offset(1 << 40)
+    path = str(tmp_path / "random.bin").encode()
+    stream = libc.fopen(path, b"wb")
+    assert lib.pumas_context_random_dump(a._ptr, stream) == 0
+    libc.fclose(stream)
+    assert len(open(path, "rb").read()) == 4 + 16
+
+    b = pb.Context(physics, seed=1)
+    stream = libc.fopen(path, b"rb")
+    assert lib.pumas_context_random_load(b._ptr, stream) == 0
+    libc.fclose(stream)
+    seed = ctypes.c_ulong()
+    assert lib.pumas_context_random_seed_get(b._ptr, ctypes.byref(seed)) == 0
+    assert seed.value == 123456789
+    # and the offset: a second dump is byte identical
+    other = str(tmp_path / "other.bin").encode()
+    stream = libc.fopen(other, b"wb")
+    assert lib.pumas_context_random_dump(b._ptr, stream) == 0
+    libc.fclose(stream)
+    assert open(other, "rb").read() == open(path, "rb").read()
+
+    assert lib.pumas_context_random_dump(a._ptr, None) == 17  # PATH_ERROR
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"\x01\x00\x00\x00" + b"\x00" * 16)
+    stream = libc.fopen(str(bad).encode(), b"rb")
+    assert lib.pumas_context_random_load(b._ptr, stream) == 11  # FORMAT_ERROR
+    libc.fclose(stream)
+    bad.write_bytes(b"\x00\xb2\x00\x00" + b"\x00" * 4)
+    stream = libc.fopen(str(bad).encode(), b"rb")
+    assert lib.pumas_context_random_load(b._ptr, stream) == 10  # IO_ERROR
+    libc.fclose(stream)
