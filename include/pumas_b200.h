@@ -334,6 +334,12 @@ PUMAS_API enum pumas_return pumas_physics_material_properties(
     const struct pumas_physics * physics, int index, int * length,
     double * density, double * I, int * components, double * fractions);
 
+/* pumas.c:3446-3475: base materials and mass fractions of a composite (the
+ * last pumas_physics_composite_length materials). */
+PUMAS_API enum pumas_return pumas_physics_composite_properties(
+    const struct pumas_physics * physics, int material, int * length,
+    int * components, double * fractions);
+
 /* pumas.c:3486-3625 */
 PUMAS_API enum pumas_return pumas_physics_table_value(
     const struct pumas_physics * physics, enum pumas_property property,

@@ -345,6 +345,7 @@ const char * pumas_error_function(pumas_function_t * caller)
         NAME(pumas_physics_material_name)
         NAME(pumas_physics_material_index)
         NAME(pumas_physics_material_properties)
+        NAME(pumas_physics_composite_properties)
         NAME(pumas_physics_table_value)
         NAME(pumas_physics_table_index)
         NAME(pumas_context_create)
@@ -761,6 +762,32 @@ int pumas_physics_material_length(const struct pumas_physics * physics)
 int pumas_physics_composite_length(const struct pumas_physics * physics)
 {
         return (physics == nullptr) ? 0 : physics->host.view.n_composites;
+}
+
+/* pumas.c:3446-3475 */
+enum pumas_return pumas_physics_composite_properties(
+    const struct pumas_physics * physics, int material, int * length,
+    int * components, double * fractions)
+{
+        if (physics == nullptr)
+                return RAISE(pumas_physics_composite_properties,
+                    PUMAS_RETURN_PHYSICS_ERROR,
+                    "the Physics has not been initialised");
+        const pb::Physics & p = physics->host.view;
+        const int i0 = p.n_materials - p.n_composites;
+        if ((material < i0) || (material > p.n_materials - 1) ||
+            ((size_t)(material - i0) >= physics->host.composite.size()))
+                return RAISE(pumas_physics_composite_properties,
+                    PUMAS_RETURN_INDEX_ERROR, "invalid material index [%d]",
+                    material);
+        const std::vector<std::pair<int, double> > & parts =
+            physics->host.composite[material - i0];
+        if (length != nullptr) *length = (int)parts.size();
+        for (size_t i = 0; i < parts.size(); i++) {
+                if (components != nullptr) components[i] = parts[i].first;
+                if (fractions != nullptr) fractions[i] = parts[i].second;
+        }
+        return PUMAS_RETURN_SUCCESS;
 }
 
 enum pumas_return pumas_physics_material_properties(

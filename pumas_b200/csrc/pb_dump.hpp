@@ -105,6 +105,9 @@ struct HostPhysics {
         std::vector<std::string> material_name;
         std::vector<std::string> element_name;
         std::vector<double> material_I;
+        /* struct composite_material of the composites (pumas.c:536-550):
+         * base material index and mass fraction of every component. */
+        std::vector<std::vector<std::pair<int, double> > > composite;
         std::string model[3];
         int model_index[3];
         int n_energy_loss_header;
@@ -348,6 +351,46 @@ inline int load_physics_bytes(
                 if (ok && (comp_element.size() != nc)) {
                         err = "corrupted binary dump (n_components)";
                         return 11;
+                }
+        }
+
+        /* Composite materials: `composite` is an array of pointers to
+         * { int n_components; struct { int material; double fraction; }[] }
+         * (pumas.c:536-550, rebased like pumas.c:2115-2119). Host side
+         * information only (pumas_physics_composite_properties). */
+        hp.composite.clear();
+        if (h.n_composites > 0) {
+                const size_t ncomp = (size_t)h.n_composites;
+                if (ncomp > nm) {
+                        err = "corrupted binary dump (n_composites)";
+                        return 11;
+                }
+                const size_t otab = off(h.composite, ncomp * 8);
+                for (size_t k = 0; ok && (k < ncomp); k++) {
+                        uint64_t pc;
+                        std::memcpy(&pc, blob + otab + 8 * k, 8);
+                        const size_t o = off(pc, 8);
+                        if (!ok) break;
+                        int32_t n_in;
+                        std::memcpy(&n_in, blob + o, 4);
+                        if ((n_in < 1) || ((size_t)n_in > nm)) {
+                                err = "corrupted binary dump (composite)";
+                                return 11;
+                        }
+                        const size_t oc = off(pc, 8 + (size_t)n_in * 16);
+                        if (!ok) break;
+                        std::vector<std::pair<int, double> > parts;
+                        for (int i = 0; i < n_in; i++) {
+                                int32_t material;
+                                double fraction;
+                                std::memcpy(&material,
+                                    blob + oc + 8 + 16 * i, 4);
+                                std::memcpy(&fraction,
+                                    blob + oc + 16 + 16 * i, 8);
+                                parts.push_back(
+                                    std::make_pair((int)material, fraction));
+                        }
+                        hp.composite.push_back(parts);
                 }
         }
 

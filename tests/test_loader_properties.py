@@ -218,3 +218,37 @@ def test_random_dump_and_load(physics, tmp_path):
     stream = libc.fopen(str(bad).encode(), b"rb")
     assert lib.pumas_context_random_load(b._ptr, stream) == 10  # IO_ERROR
     libc.fclose(stream)
+
+
+def test_composite_properties(physics, oracle):
+    """pumas_physics_composite_properties (pumas.c:3446): WetRock of
+    examples/data/materials.xml, against the reference."""
+    import ctypes
+    ours, ref = pb.library(), oracle.lib
+    for lib in (ours, ref):
+        lib.pumas_physics_composite_properties.argtypes = [
+            ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+            ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]
+        lib.pumas_physics_composite_length.argtypes = [ctypes.c_void_p]
+        lib.pumas_physics_material_length.argtypes = [ctypes.c_void_p]
+    n = ours.pumas_physics_material_length(physics._handle)
+    nc = ours.pumas_physics_composite_length(physics._handle)
+    assert (n, nc) == (ref.pumas_physics_material_length(oracle.physics),
+                       ref.pumas_physics_composite_length(oracle.physics))
+    assert nc == 1
+    for material in range(n - nc, n):
+        got = []
+        for lib, handle in ((ours, physics._handle), (ref, oracle.physics)):
+            length = ctypes.c_int()
+            assert lib.pumas_physics_composite_properties(
+                handle, material, ctypes.byref(length), None, None) == 0
+            components = (ctypes.c_int * length.value)()
+            fractions = (ctypes.c_double * length.value)()
+            assert lib.pumas_physics_composite_properties(
+                handle, material, None, components, fractions) == 0
+            got.append((length.value, list(components), list(fractions)))
+        assert got[0] == got[1] and got[0][0] == 2
+        assert abs(sum(got[0][2]) - 1.) < 1e-12
+    # a base material is not a composite (pumas.c:3456-3459)
+    assert ours.pumas_physics_composite_properties(
+        physics._handle, 0, None, None, None) == 7
