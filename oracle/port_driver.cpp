@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "pb_dump.hpp"
+#include "pb_hot.h"
 #include "pb_transport.h"
 #include "philox.h"
 #include "pumas_b200.h"
@@ -61,7 +62,8 @@ struct Job {
 };
 
 /* 1: use the compile time specialised instantiations the GPU library uses
- * (pumas_b200/csrc/kernels_spec*.cu) when the configuration matches; 0: the
+ * (pumas_b200/csrc/kernels_spec*.cu) when the configuration matches; 2: the
+ * same through the lean step of pb_hot.h (what the GPU runs for them); 0: the
  * general instantiation only. */
 int g_specialise = 1;
 
@@ -86,6 +88,61 @@ void run_tracks(Job * job, const Cfg & cfg, const Geo & geo)
         }
 }
 
+/* The lean step of the GPU kernels (pb_hot.h) chained with the general event
+ * handlers, through the slot packing the kernel uses. */
+template <class Cfg>
+void run_tracks_hot(Job * job, const Cfg & cfg, const pb::UniformGeometry & geo)
+{
+        using namespace pb;
+        const Physics & p = job->hp->view;
+        std::vector<double> tables(hot_tables_words(p));
+        double * const hotK = tables.data();
+        double * const hotX = hotK +
+            (size_t)p.n_materials * (p.n_energies - 1) * HOTK_WORDS;
+        hot_tables_build(p, hotK, hotX);
+        const HotCtx h = hot_context(p, p, hotK, hotX, cfg, geo.material);
+        for (long i = job->begin; i < job->end; i++) {
+                PhiloxRng rng;
+                pb_philox_init(&rng.g, job->seed, job->offset + (uint64_t)i);
+                State & state = job->states[i];
+                const double charge = state.charge;
+                Outcome out;
+                Track trk;
+                Loop lp;
+                int phase = track_begin(p, cfg, geo, rng, state, trk, lp, out);
+                if (phase != PHASE_DONE) {
+                        PlainSlot s;
+                        hot_pack(s, state, trk, lp, phase, false, 0.);
+                        while (phase != PHASE_DONE) {
+                                if (phase == PHASE_STEP) {
+                                        phase = hot_step(p, cfg, geo, h, s, rng);
+                                        continue;
+                                }
+                                hot_unpack(s, p, cfg, geo, state, trk, lp);
+                                trk.step_X_limit = h.step_X_limit;
+                                if (phase == PHASE_EHS)
+                                        phase = stepping_ehs(
+                                            p, cfg, geo, trk, rng, state, lp);
+                                else
+                                        phase = stepping_del(
+                                            p, cfg, geo, trk, rng, state, lp);
+                                hot_pack(s, state, trk, lp, phase, false, 0.);
+                        }
+                        hot_unpack(s, p, cfg, geo, state, trk, lp);
+                        state.charge = charge;
+                        track_end(trk, lp, out);
+                }
+                if ((out.rc != 0) && (job->rc == 0)) job->rc = out.rc;
+                if (job->events) job->events[i] = out.event;
+                if (job->media) {
+                        job->media[2 * i] = out.medium[0];
+                        job->media[2 * i + 1] = out.medium[1];
+                }
+                if (job->n_random) job->n_random[i] = rng.g.count;
+                if (job->n_steps) job->n_steps[i] = trk.n_steps;
+        }
+}
+
 template <int EL, int SC, int DI, int DE> bool try_specialised(Job * job)
 {
         typedef pb::StaticSettings<EL, SC, DI, DE> Cfg;
@@ -96,7 +153,10 @@ template <int EL, int SC, int DI, int DE> bool try_specialised(Job * job)
         pb::UniformGeometry ug;
         ug.material = geo.layer[0].material;
         ug.step_type = geo.step_type;
-        run_tracks(job, Cfg(job->cfg), ug);
+        if (g_specialise == 2)
+                run_tracks_hot(job, Cfg(job->cfg), ug);
+        else
+                run_tracks(job, Cfg(job->cfg), ug);
         return true;
 }
 

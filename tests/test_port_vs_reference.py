@@ -4,8 +4,9 @@ reference itself (oracle/_ref), track by track with the same Philox streams.
 
 With the same libm and no FMA contraction on either side the restatement is
 expected to be BIT EXACT, including the number of variates each track draws.
-Both the general instantiation and the compile-time specialised ones that the
-GPU library dispatches to are covered, and the double-double replacement of
+The general instantiation, the compile-time specialised ones and the lean
+step of pb_hot.h (mode 2: what the GPU library runs for the straggled mode in a
+uniform medium, through the same slot packing) are covered, and the double-double replacement of
 the reference's x87 long double arithmetic (pb_dd.h)."""
 import os
 
@@ -39,7 +40,7 @@ def test_bit_exact(name):
         w["settings"], w["geometry"], w["states"], seed=3, offset=17,
         threads=THREADS)
     assert rc == 0
-    for engine, specialise in ((port, 1), (port, 0), (port_dd, 1)):
+    for engine, specialise in ((port, 1), (port, 0), (port, 2), (port_dd, 1)):
         engine.lib.port_set_specialise(specialise)
         sp, ep, mp, rp, steps, rcp = engine.transport(
             w["settings"], w["geometry"], w["states"], seed=3, offset=17,
