@@ -439,11 +439,14 @@ PUMAS_API enum pumas_return pumas_b200_context_track_offset_set(
 PUMAS_API enum pumas_return pumas_b200_context_stream_set(
     struct pumas_context * context, void * cuda_stream);
 
-/* New. Select the device kernel: 0 (default) the resident kernel, persistent
- * CTAs whose lanes keep their track in registers and regroup tracks by pending
- * event; 1 the monolithic kernel, one thread per track for its whole life
- * (kept for A/B parity and profiling); 2 the resident kernel without compile
- * time specialisation. All give the same per-track results. */
+/* New. Select the device kernel: 0 (default) the persistent kernels that
+ * regroup tracks by pending event: tracks resident in shared memory for the
+ * straggled mode in a uniform medium (hot_kernel.cuh), in registers otherwise
+ * (resident.cuh); 1 the monolithic kernel, one thread per track for its whole
+ * life (kept for A/B parity and profiling); 2 the register resident kernel
+ * without compile time specialisation; 3 the register resident kernel with
+ * its specialisations (round 1 product path, A/B). All give the same
+ * per-track results. */
 PUMAS_API enum pumas_return pumas_b200_context_kernel_set(
     struct pumas_context * context, int kernel);
 

@@ -29,6 +29,11 @@ namespace {
 struct PhiloxRng {
         pb_philox g;
         double uniform() { return pb_philox_uniform(&g); }
+        /* (the interface of the lean step, pb_hot.h) */
+        double uniform_fast() { return uniform(); }
+        double uniform_keep() { return uniform(); }
+        double log_uniform_fast() { return pb::xlog(uniform()); }
+        double log_uniform_keep() { return pb::xlog(uniform()); }
 };
 
 pb::Settings settings_from(const struct pumas_context * c)
@@ -95,12 +100,8 @@ void run_tracks_hot(Job * job, const Cfg & cfg, const pb::UniformGeometry & geo)
 {
         using namespace pb;
         const Physics & p = job->hp->view;
-        std::vector<double> tables(hot_tables_words(p));
-        double * const hotK = tables.data();
-        double * const hotX = hotK +
-            (size_t)p.n_materials * (p.n_energies - 1) * HOTK_WORDS;
-        hot_tables_build(p, hotK, hotX);
-        const HotCtx h = hot_context(p, p, hotK, hotX, cfg, geo.material);
+        /* (the packed tables the dump loader built) */
+        const HotCtx h = hot_context(p, p, p.hotK, p.hotX, cfg, geo.material);
         for (long i = job->begin; i < job->end; i++) {
                 PhiloxRng rng;
                 pb_philox_init(&rng.g, job->seed, job->offset + (uint64_t)i);
@@ -118,14 +119,14 @@ void run_tracks_hot(Job * job, const Cfg & cfg, const pb::UniformGeometry & geo)
                                         phase = hot_step(p, cfg, geo, h, s, rng);
                                         continue;
                                 }
+                                if (phase == PHASE_EHS) {
+                                        phase = hot_ehs(p, cfg, geo, h, s, rng);
+                                        continue;
+                                }
                                 hot_unpack(s, p, cfg, geo, state, trk, lp);
                                 trk.step_X_limit = h.step_X_limit;
-                                if (phase == PHASE_EHS)
-                                        phase = stepping_ehs(
-                                            p, cfg, geo, trk, rng, state, lp);
-                                else
-                                        phase = stepping_del(
-                                            p, cfg, geo, trk, rng, state, lp);
+                                phase = stepping_del(
+                                    p, cfg, geo, trk, rng, state, lp);
                                 hot_pack(s, state, trk, lp, phase, false, 0.);
                         }
                         hot_unpack(s, p, cfg, geo, state, trk, lp);

@@ -1160,7 +1160,7 @@ enum pumas_return pumas_b200_context_kernel_set(
                 return RAISE(pumas_b200_context_kernel_set,
                     PUMAS_RETURN_VALUE_ERROR, "no context (null)");
         if ((kernel < pb::KERNEL_RESIDENT) ||
-            (kernel > pb::KERNEL_RESIDENT_GENERAL))
+            (kernel > pb::KERNEL_RESIDENT_SPEC))
                 return RAISE(pumas_b200_context_kernel_set,
                     PUMAS_RETURN_INDEX_ERROR, "invalid kernel index [%d]",
                     kernel);
@@ -1273,7 +1273,8 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
                 e = cudaMemsetAsync(c->d_status, 0, sizeof(int), stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev0, stream);
         if (e == cudaSuccess)
-                e = pb::launch_transport(physics->d_view, cfg, c->geometry,
+                e = pb::launch_transport(physics->d_view, physics->host.view, cfg,
+                    c->geometry,
                     (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_states,
                     d_events, d_media, c->d_status, c->d_random, c->d_steps,
                     c->d_workspace, c->kernel, stream);

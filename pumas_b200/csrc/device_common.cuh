@@ -119,6 +119,8 @@ struct BatchArgs {
         unsigned long long * stats;  /* optional scheduler statistics */
         int ehs_period;    /* the warp pools are served every that many rounds */
         int del_threshold; /* events queued before a DEL warp starts a pass */
+        int service_patience; /* polls (2 us each) a service warp waits for
+                               * that many before it serves what there is */
 };
 
 constexpr int N_STATS = 16;
@@ -129,13 +131,14 @@ struct Tunables {
         int ehs_period, del_threshold; /* <= 0: the kernel's default */
         int grid_cap;                  /* <= 0: one CTA per SM */
         int del_ctas;                  /* <= 0: the launcher's choice */
+        int service_patience;          /* <= 0: the kernel's default */
         unsigned long long * stats;
         int sms;
 };
 
 inline const Tunables & tunables()
 {
-        static Tunables t = { 0, 0, 0, 0, nullptr, 0 };
+        static Tunables t = { 0, 0, 0, 0, 0, nullptr, 0 };
         if (t.sms != 0) return t;
         const char * v;
         if ((v = getenv("PUMAS_B200_EHS_PERIOD")) != nullptr)
@@ -145,6 +148,8 @@ inline const Tunables & tunables()
         if ((v = getenv("PUMAS_B200_GRID")) != nullptr) t.grid_cap = atoi(v);
         if ((v = getenv("PUMAS_B200_DEL_CTAS")) != nullptr)
                 t.del_ctas = atoi(v);
+        if ((v = getenv("PUMAS_B200_SERVICE_PATIENCE")) != nullptr)
+                t.service_patience = atoi(v);
         if (getenv("PUMAS_B200_STATS") != nullptr)
                 cudaMalloc(&t.stats, N_STATS * sizeof *t.stats);
         int dev = 0;
@@ -163,8 +168,9 @@ inline int & last_launch_count()
 
 /* The workspace holds the global work cursor and, for the kernels that hand
  * the hard inelastic events over to dedicated CTAs (resident.cuh,
- * PB_RS_OFFLOAD), their queues and parking area. */
-constexpr size_t WORKSPACE_BYTES = (size_t)4 << 20;
+ * PB_RS_OFFLOAD; hot_kernel.cuh), their queues and parking area / the mirrors
+ * of the slots. */
+constexpr size_t WORKSPACE_BYTES = (size_t)32 << 20;
 inline size_t workspace_bytes() { return WORKSPACE_BYTES; }
 
 } /* namespace pb */

@@ -52,6 +52,19 @@ PB_SPECIALISATION(launch_spec_straggled_noscat_forward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_backward);
 PB_SPECIALISATION(launch_spec_csda);
 
+/* hot_kernel.cuh instantiations (kernels_hot*.cu) */
+#define PB_HOT_SPECIALISATION(NAME)                                            \
+        bool NAME(const Physics & p, const Physics & host_view,                \
+            const Settings & cfg, const Geometry & geo, uint64_t seed,         \
+            uint64_t offset, long n, State * states, int * events,             \
+            int * media, int * status, unsigned int * n_random,                \
+            unsigned int * n_steps, void * workspace, cudaStream_t stream,     \
+            cudaError_t * error)
+PB_HOT_SPECIALISATION(launch_hot_straggled_mixed_forward);
+PB_HOT_SPECIALISATION(launch_hot_straggled_mixed_backward);
+PB_HOT_SPECIALISATION(launch_hot_straggled_noscat_forward);
+PB_HOT_SPECIALISATION(launch_hot_straggled_noscat_backward);
+
 int transport_last_launches() { return last_launch_count(); }
 
 cudaError_t transport_workspace_bytes(size_t * bytes)
@@ -60,8 +73,8 @@ cudaError_t transport_workspace_bytes(size_t * bytes)
         return cudaSuccess;
 }
 
-cudaError_t launch_transport(const Physics & p, const Settings & cfg,
-    const Geometry & geo, uint64_t seed, uint64_t offset, long n,
+cudaError_t launch_transport(const Physics & p, const Physics & host_view,
+    const Settings & cfg, const Geometry & geo, uint64_t seed, uint64_t offset, long n,
     State * states, int * events, int * media, int * status,
     unsigned int * n_random, unsigned int * n_steps, void * workspace,
     int kernel, cudaStream_t stream)
@@ -77,6 +90,18 @@ cudaError_t launch_transport(const Physics & p, const Settings & cfg,
         }
 
         if (kernel == KERNEL_RESIDENT) {
+                cudaError_t e = cudaSuccess;
+#define TRY_HOT(NAME)                                                          \
+        if (NAME(p, host_view, cfg, geo, seed, offset, n, states, events,      \
+                media, status, n_random, n_steps, workspace, stream, &e))      \
+                return e;
+                TRY_HOT(launch_hot_straggled_mixed_forward)
+                TRY_HOT(launch_hot_straggled_mixed_backward)
+                TRY_HOT(launch_hot_straggled_noscat_forward)
+                TRY_HOT(launch_hot_straggled_noscat_backward)
+#undef TRY_HOT
+        }
+        if ((kernel == KERNEL_RESIDENT) || (kernel == KERNEL_RESIDENT_SPEC)) {
                 cudaError_t e = cudaSuccess;
 #define TRY(NAME)                                                              \
         if (NAME(p, cfg, geo, seed, offset, n, states, events, media, status,  \

@@ -21,7 +21,11 @@ enum {
         /* one thread runs one track to completion */
         KERNEL_MONOLITHIC = 1,
         /* the resident kernel, general instantiation only */
-        KERNEL_RESIDENT_GENERAL = 2
+        KERNEL_RESIDENT_GENERAL = 2,
+        /* the register resident kernel with its specialised instantiations,
+         * without the shared memory resident kernel (hot_kernel.cuh) that
+         * KERNEL_RESIDENT tries first (A/B) */
+        KERNEL_RESIDENT_SPEC = 3
 };
 
 /* Size of the device scratch buffer launch_transport needs (work cursor and
@@ -31,12 +35,14 @@ cudaError_t transport_workspace_bytes(size_t * bytes);
  * the DEL CTAs are prepared by resident_offload_init). */
 int transport_last_launches();
 
-/* Transport n tracks. All pointers are device pointers; `status` receives the
+/* Transport n tracks. `p` is the device view of the physics tables and
+ * `host_view` the host one (per launch constants are read from it). All
+ * other pointers are device pointers; `status` receives the
  * first non-zero pumas_return raised by a track, `workspace` is a scratch
  * buffer of transport_workspace_bytes(). Track i draws from the Philox stream
  * (seed, offset + i). */
-cudaError_t launch_transport(const Physics & p, const Settings & cfg,
-    const Geometry & geo, uint64_t seed, uint64_t offset, long n,
+cudaError_t launch_transport(const Physics & p, const Physics & host_view,
+    const Settings & cfg, const Geometry & geo, uint64_t seed, uint64_t offset, long n,
     State * states, int * events, int * media, int * status,
     unsigned int * n_random, unsigned int * n_steps, void * workspace,
     int kernel, cudaStream_t stream);

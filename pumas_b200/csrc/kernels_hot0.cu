@@ -1,0 +1,12 @@
+/*
+ * kernels_hot0.cu -- shared memory resident kernel (hot_kernel.cuh) for
+ * (STRAGGLED, MODE_MIXED, MODE_FORWARD, WEIGHTED) in a single infinite medium without locals
+ * (examples/pumas/straight.c geometry).
+ */
+#include "hot_kernel.cuh"
+
+namespace pb {
+
+PB_DEFINE_HOT_SPECIALISATION(launch_hot_straggled_mixed_forward, MODE_STRAGGLED, MODE_MIXED, MODE_FORWARD, MODE_WEIGHTED)
+
+} /* namespace pb */

@@ -115,7 +115,9 @@ PB_FN double coulomb_nuclear_form_factor(double mu, double N)
                 d = 1. / (1. + 0.1 * x2);
         } else {
                 const double x = sqrt(x2);
-                d = 3 * (xsin(x) - x * xcos(x)) / (x2 * x);
+                /* (one argument reduction for both; same values) */
+                const SinCos sc = xsincos(x);
+                d = 3 * (sc.s - x * sc.c) / (x2 * x);
         }
         return d * d;
 }

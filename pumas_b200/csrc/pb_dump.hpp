@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "pb_atomic_data.h"
+#include "pb_hot_tables.h"
 #include "pb_physics.h"
 
 namespace pb {
@@ -421,7 +422,15 @@ inline int load_physics_bytes(
         const size_t o_cel = detail::align16(o_coff + (nm + 1) * 4);
         const size_t o_cfr = detail::align16(o_cel + nc * 4);
         const size_t o_elt = detail::align16(o_cfr + nc * 8);
-        const size_t total = detail::align16(o_elt + nel * sizeof(Element));
+        /* the per cell records of the lean step (pb_hot_tables.h), 256 byte
+         * aligned: a record never straddles a 128 byte line pair */
+        const size_t n_cells = (ne > 0) ? (size_t)(ne - 1) : 0;
+        const size_t o_hotK =
+            (detail::align16(o_elt + nel * sizeof(Element)) + 255) &
+            ~(size_t)255;
+        const size_t o_hotX = o_hotK + nm * n_cells * HOTK_WORDS * sizeof(double);
+        const size_t total = detail::align16(
+            o_hotX + nm * n_cells * HOTX_WORDS * sizeof(double));
         hp.image.assign(total, 0);
         std::memcpy(hp.image.data() + o_blob, blob, size);
         std::memcpy(hp.image.data() + o_coff, comp_offset.data(), (nm + 1) * 4);
@@ -515,12 +524,17 @@ inline int load_physics_bytes(
         PB_RELOC(comp_element, o_cel);
         PB_RELOC(comp_fraction, o_cfr);
         PB_RELOC(element, o_elt);
+        PB_RELOC(hotK, o_hotK);
+        PB_RELOC(hotX, o_hotX);
 #undef PB_RELOC
         if (!ok) {
                 err = "corrupted binary dump (pointer outside of the blob)";
                 return 11;
         }
         hp.view = hp.view_at(hp.image.data());
+        hot_tables_build(hp.view,
+            reinterpret_cast<double *>(hp.image.data() + o_hotK),
+            reinterpret_cast<double *>(hp.image.data() + o_hotX));
         return 0;
 }
 

@@ -37,97 +37,17 @@
 
 #include <cstring>
 
+#include "pb_hot_math.h"
+#include "pb_hot_tables.h"
 #include "pb_transport.h"
 
 namespace pb {
 
-/* ---- packed tables --------------------------------------------------------
- * K record of cell i (kinetic grid, material m, straggled / mixed scheme):
- *   [0] K[i]  [1] K[i+1]  [2] K[i+1]-K[i]  [3] Lb[i]
- *   [4..7] X  [8..11] Omega  [12..15] CS  [16..19] Ms1  [20..23] dE
- *   [24..27] Mu0   [28] Lb[i+1]-Lb[i]   [29..31] unused
- * X record of cell i (grammage column of the same scheme and material):
- *   [0] X[i]  [1] X[i+1]  [2] X[i+1]-X[i]  [3] unused  [4..7] K
- * each column as (p0, m0 * dx, c2, c3). */
-constexpr int HOTK_WORDS = 32;
-constexpr int HOTX_WORDS = 8;
-constexpr int HK_X = 4, HK_OMEGA = 8, HK_CS = 12, HK_MS1 = 16, HK_DE = 20,
-              HK_MU0 = 24, HK_DLB = 28;
-constexpr int HX_K = 4;
-
-/* The four coefficients of one cell of one column: table_interpolate_pchip
- * (pumas.c:4146-4157) up to the evaluation of the polynomial. */
-inline void hot_pack_column(const double * table_Y, const double * table_M,
-    int i1, double dX, double * out)
-{
-        const int i2 = i1 + 1;
-        const double m1 = table_M[i1] * dX;
-        const double m2 = (i2 > 1) ? table_M[i2] * dX : m1;
-        const double p0 = table_Y[i1], p1 = table_Y[i2];
-        /* math_pchip_interpolate, pumas.c:4118-4125 */
-        const double c2 = -3 * (p0 - p1) - 2 * m1 - m2;
-        const double c3 = 2 * (p0 - p1) + m1 + m2;
-        out[0] = p0;
-        out[1] = m1;
-        out[2] = c2;
-        out[3] = c3;
-}
-
-/* Number of doubles of the packed tables of a physics object. */
-inline size_t hot_tables_words(const Physics & p)
-{
-        return (size_t)p.n_materials * (size_t)(p.n_energies - 1) *
-            (HOTK_WORDS + HOTX_WORDS);
-}
-
-/* Fill the packed tables (host, at load time): first the K records of every
- * material, then the X records. Scheme index MODE_MIXED: the tables the
- * straggled and mixed modes read (pumas.c:4260-4281, 4684). */
-inline void hot_tables_build(const Physics & p, double * hotK, double * hotX)
-{
-        const int nc = p.n_energies - 1;
-        const int scheme = MODE_MIXED;
-        for (int m = 0; m < p.n_materials; m++) {
-                const double * X = col_sm(p, p.X, scheme, m);
-                for (int i = 0; i < nc; i++) {
-                        double * r =
-                            hotK + ((size_t)m * nc + i) * HOTK_WORDS;
-                        for (int k = 0; k < HOTK_WORDS; k++) r[k] = 0.;
-                        const double dK = p.K[i + 1] - p.K[i];
-                        r[0] = p.K[i];
-                        r[1] = p.K[i + 1];
-                        r[2] = dK;
-                        r[3] = col_m(p, p.Lb, m)[i];
-                        hot_pack_column(
-                            X, col_sm(p, p.X_dK, scheme, m), i, dK, r + HK_X);
-                        hot_pack_column(col_m(p, p.Omega, m),
-                            col_m(p, p.Omega_dK, m), i, dK, r + HK_OMEGA);
-                        hot_pack_column(col_m(p, p.CS, m), col_m(p, p.CS_dK, m),
-                            i, dK, r + HK_CS);
-                        hot_pack_column(col_Ms1(p, p.Ms1, scheme, m),
-                            col_Ms1(p, p.Ms1_dK, scheme, m), i, dK,
-                            r + HK_MS1);
-                        hot_pack_column(col_sm(p, p.dE, scheme, m),
-                            col_sm(p, p.dE_dK, scheme, m), i, dK, r + HK_DE);
-                        hot_pack_column(col_m(p, p.Mu0, m),
-                            col_m(p, p.Mu0_dK, m), i, dK, r + HK_MU0);
-                        r[HK_DLB] =
-                            col_m(p, p.Lb, m)[i + 1] - col_m(p, p.Lb, m)[i];
-
-                        double * q =
-                            hotX + ((size_t)m * nc + i) * HOTX_WORDS;
-                        for (int k = 0; k < HOTX_WORDS; k++) q[k] = 0.;
-                        const double dX = X[i + 1] - X[i];
-                        q[0] = X[i];
-                        q[1] = X[i + 1];
-                        q[2] = dX;
-                        hot_pack_column(p.K, col_sm(p, p.K_dX, scheme, m), i,
-                            dX, q + HX_K);
-                }
-        }
-}
-
-/* ---- loads ---------------------------------------------------------------- */
+/* ---- loads -----------------------------------------------------------------
+ * A `HotPtr` addresses a word of the packed tables: a pointer (CPU build;
+ * kernels that read them from HBM through L1), or, with PB_HOT_SMEM_TABLES (set
+ * by hot_kernel.cuh), a 64 bit word index into the CTA's shared memory, where
+ * the kernel stages the records of the medium's material (50 KB). */
 struct D2 {
         double x, y;
 };
@@ -135,7 +55,64 @@ struct D4 {
         double a, b, c, d;
 };
 
-PB_FN D2 hot_ld2(const double * p)
+#if defined(__CUDACC__) && defined(PB_HOT_SMEM_TABLES)
+typedef unsigned int HotPtr;
+extern __shared__ __align__(16) unsigned long long hot_smem64[];
+
+PB_FN double hot_ld1(HotPtr p)
+{
+#if defined(__CUDA_ARCH__)
+        return __longlong_as_double((long long)hot_smem64[p]);
+#else
+        (void)p;
+        return 0.;
+#endif
+}
+
+PB_FN D2 hot_ld2(HotPtr p)
+{
+        D2 r;
+#if defined(__CUDA_ARCH__)
+        const double2 v = *reinterpret_cast<const double2 *>(&hot_smem64[p]);
+        r.x = v.x;
+        r.y = v.y;
+#else
+        (void)p;
+        r.x = r.y = 0.;
+#endif
+        return r;
+}
+
+PB_FN D4 hot_ld4(HotPtr p)
+{
+        D4 r;
+#if defined(__CUDA_ARCH__)
+        const double2 u = *reinterpret_cast<const double2 *>(&hot_smem64[p]);
+        const double2 v =
+            *reinterpret_cast<const double2 *>(&hot_smem64[p + 2]);
+        r.a = u.x;
+        r.b = u.y;
+        r.c = v.x;
+        r.d = v.y;
+#else
+        (void)p;
+        r.a = r.b = r.c = r.d = 0.;
+#endif
+        return r;
+}
+#else
+typedef const double * HotPtr;
+
+PB_FN double hot_ld1(HotPtr p)
+{
+#if defined(__CUDA_ARCH__)
+        return __ldg(p);
+#else
+        return *p;
+#endif
+}
+
+PB_FN D2 hot_ld2(HotPtr p)
 {
         D2 r;
 #if defined(__CUDA_ARCH__)
@@ -149,7 +126,7 @@ PB_FN D2 hot_ld2(const double * p)
         return r;
 }
 
-PB_FN D4 hot_ld4(const double * p)
+PB_FN D4 hot_ld4(HotPtr p)
 {
         D4 r;
 #if defined(__CUDA_ARCH__)
@@ -167,9 +144,10 @@ PB_FN D4 hot_ld4(const double * p)
 #endif
         return r;
 }
+#endif
 
 /* A packed column at reduced abscissa t: the polynomial of pumas.c:4124. */
-PB_FN double hot_pchip(const double * column, double t)
+PB_FN double hot_pchip(HotPtr column, double t)
 {
         const D4 c = hot_ld4(column);
         return c.a + t * (c.b + t * (c.c + t * c.d));
@@ -177,12 +155,16 @@ PB_FN double hot_pchip(const double * column, double t)
 
 /* ---- per launch constants ------------------------------------------------- */
 struct HotCtx {
-        const double * hotK; /* K records of the medium's material */
-        const double * hotX; /* X records of the same */
+        HotPtr hotK; /* K records of the medium's material */
+        HotPtr hotX; /* X records of the same */
+        /* the same in HBM (the kernels that stage them to shared memory) */
+        const double * gK;
+        const double * gX;
         int n_cells;         /* n_energies - 1 */
         int material;
         double K0, K1, Kmax; /* K[0], K[1], K[n_energies - 1] */
         double X0, Xmax;     /* grammage column: first and last node */
+        double Ms1_1, Lb_1;  /* Ms1[1], Lb[1]: below K[1], pumas.c:4088, 7453 */
         double density, density_i;
         double mass, ctau;
         double step_X_limit; /* pumas.c:5262-5266, constant in one material */
@@ -200,8 +182,14 @@ inline HotCtx hot_context(const Physics & host_view, const Physics & view,
         HotCtx h;
         const Physics & p = host_view;
         const int nc = p.n_energies - 1;
-        h.hotK = hotK + (size_t)material * nc * HOTK_WORDS;
-        h.hotX = hotX + (size_t)material * nc * HOTX_WORDS;
+        h.gK = hotK + (size_t)material * nc * HOTK_WORDS;
+        h.gX = hotX + (size_t)material * nc * HOTX_WORDS;
+#if defined(__CUDACC__) && defined(PB_HOT_SMEM_TABLES)
+        h.hotK = h.hotX = 0; /* (set by the launcher: shared memory layout) */
+#else
+        h.hotK = h.gK;
+        h.hotX = h.gX;
+#endif
         h.n_cells = nc;
         h.material = material;
         h.K0 = p.K[0];
@@ -210,6 +198,8 @@ inline HotCtx hot_context(const Physics & host_view, const Physics & view,
         const double * X = col_sm(p, p.X, MODE_MIXED, material);
         h.X0 = X[0];
         h.Xmax = X[nc];
+        h.Ms1_1 = col_Ms1(p, p.Ms1, MODE_MIXED, material)[1];
+        h.Lb_1 = col_m(p, p.Lb, material)[1];
         h.density = p.material_density[material];
         h.density_i = 1. / h.density;
         h.mass = p.mass;
@@ -365,92 +355,144 @@ struct HLoc {
 /* Cell of x in the kinetic grid, walking from `hint`. Requires K0 <= x < Kmax
  * (the caller checks): on a strictly increasing grid this is the cell the
  * reference's bisection returns (pumas.c:4174-4233). */
-PB_FN HLoc hot_locate_K(const HotCtx & h, double x, int hint)
+PB_HOTCALL HLoc hot_locate_K(const HotCtx & h, double x, int hint)
 {
         int i = hint;
         if (i < 0) i = 0;
         if (i > h.n_cells - 1) i = h.n_cells - 1;
-        D2 b = hot_ld2(h.hotK + (size_t)i * HOTK_WORDS);
+        D2 b = hot_ld2(h.hotK + i * HOTK_WORDS);
         while (x < b.x) {
                 --i;
-                b = hot_ld2(h.hotK + (size_t)i * HOTK_WORDS);
+                b = hot_ld2(h.hotK + i * HOTK_WORDS);
         }
         while (x >= b.y) {
                 ++i;
-                b = hot_ld2(h.hotK + (size_t)i * HOTK_WORDS);
+                b = hot_ld2(h.hotK + i * HOTK_WORDS);
         }
         HLoc l;
         l.i = i;
-        l.t = (x - b.x) / (b.y - b.x);
+        l.t = hot_div(x - b.x, b.y - b.x);
         return l;
 }
 
 /* Same in the grammage column. Requires X0 <= x < Xmax. */
-PB_FN HLoc hot_locate_X(const HotCtx & h, double x, int hint)
+PB_HOTCALL HLoc hot_locate_X(const HotCtx & h, double x, int hint)
 {
         int i = hint;
         if (i < 0) i = 0;
         if (i > h.n_cells - 1) i = h.n_cells - 1;
-        D2 b = hot_ld2(h.hotX + (size_t)i * HOTX_WORDS);
+        D2 b = hot_ld2(h.hotX + i * HOTX_WORDS);
         while (x < b.x) {
                 --i;
-                b = hot_ld2(h.hotX + (size_t)i * HOTX_WORDS);
+                b = hot_ld2(h.hotX + i * HOTX_WORDS);
         }
         while (x >= b.y) {
                 ++i;
-                b = hot_ld2(h.hotX + (size_t)i * HOTX_WORDS);
+                b = hot_ld2(h.hotX + i * HOTX_WORDS);
         }
         HLoc l;
         l.i = i;
-        l.t = (x - b.x) / (b.y - b.x);
+        l.t = hot_div(x - b.x, b.y - b.x);
         return l;
 }
 
-PB_FN const double * hot_K(const HotCtx & h, const HLoc & l)
+PB_FN HotPtr hot_K(const HotCtx & h, const HLoc & l)
 {
-        return h.hotK + (size_t)l.i * HOTK_WORDS;
+        return h.hotK + l.i * HOTK_WORDS;
 }
 
 /* cel_kinetic_energy (pumas.c:3758-3784) of a grammage inside the column. */
 PB_FN double hot_kinetic_of_grammage(const HotCtx & h, double X, int hint)
 {
         const HLoc l = hot_locate_X(h, X, hint);
-        return hot_pchip(h.hotX + (size_t)l.i * HOTX_WORDS + HX_K, l.t);
+        return hot_pchip(h.hotX + l.i * HOTX_WORDS + HX_K, l.t);
 }
 
-/* coulomb_ehs_length (pumas.c:7446-7466) at a located energy >= K[1]. */
+/* coulomb_ehs_length (pumas.c:7446-7466) at an energy located in the grid. */
 PB_FN double hot_ehs_length(
     const HotCtx & h, const HLoc & l, double kinetic)
 {
         const double p2 = kinetic * (kinetic + 2. * h.mass);
-        const double * r = hot_K(h, l);
-#if defined(__CUDA_ARCH__)
-        const double lb = __ldg(r + 3), dlb = __ldg(r + HK_DLB);
-#else
-        const double lb = r[3], dlb = r[HK_DLB];
-#endif
-        return (lb + l.t * dlb) / p2;
+        if (kinetic < h.K1) return hot_div(h.Lb_1, p2);
+        const D2 lb = hot_ld2(hot_K(h, l) + HK_LB);
+        return hot_div(lb.x + l.t * lb.y, p2);
 }
 
-/* Is the energy one the lean step handles: inside the grid, above its first
- * cell (table_get_msc and coulomb_ehs_length switch at K[1], pumas.c:4088,
- * 7453) and below the 1e9 GeV step reduction (pumas.c:6331). */
+/* Inverse first transport grammage, table_get_msc (pumas.c:4077-4111), at an
+ * energy located in the grid. */
+PB_FN double hot_msc_invlb1(const HotCtx & h, const HLoc & l, double kinetic)
+{
+        if (kinetic < h.K1)
+                return h.Ms1_1 * hot_sqrt(hot_div(h.K1, kinetic));
+        return hot_pchip(hot_K(h, l) + HK_MS1, l.t);
+}
+
+/* Is the energy inside the grid? */
+PB_FN bool hot_in_grid(const HotCtx & h, double k)
+{
+        return (k >= h.K0) && (k < h.Kmax);
+}
+
+/* Is the energy one the lean step handles: inside the grid and below the
+ * 1e9 GeV step reduction (pumas.c:6331). The stopping tracks spend a tenth of
+ * all steps below K[1] = 1 MeV (steps of STEP_MIN): the lean step covers the
+ * first cell, with the switches of table_get_msc and coulomb_ehs_length at
+ * K[1] (pumas.c:4088, 7453). */
 PB_FN bool hot_energy_ok(const HotCtx & h, double k)
 {
-        return (k >= h.K1) && (k < h.Kmax) && !(k > 1E+09);
+        return hot_in_grid(h, k) && !(k > 1E+09);
 }
 
 /* The thinning candidates of a step (pumas.c:6606-6622, 6637-6660): kinetic
- * energy at the grammage of the candidate vertex. Out of line, rare. General
- * look-ups: the energies may leave the range of the lean ones. */
+ * energy at the grammage of the candidate vertex, located in the grid when it
+ * lies there. One out of line copy for the two call sites; the look-ups walk
+ * from the cell of the start energy (the candidate lies within the step). */
+struct HotVertex {
+        double k;
+        HLoc l;
+        int located; /* K[0] <= k < Kmax: `l` is valid */
+};
+
 template <class Cfg>
-PB_NOINLINE double hot_vertex_energy(const Physics & p, const Cfg & cfg,
-    int material, double energy, double Xtot, double X_ev, double ratio)
+PB_NOINLINE HotVertex hot_vertex(const Physics & p, const Cfg & cfg,
+    const HotCtx & h, double energy, double Xtot, double X_ev, double ratio,
+    int hint)
 {
         const double sgn = (cfg.direction == MODE_FORWARD) ? 1. : -1.;
-        const double k_h = cel_kinetic_energy(
-            p, cfg.energy_loss, material, Xtot - sgn * X_ev);
-        return energy - sgn * ratio * fabs(energy - k_h);
+        const double X = Xtot - sgn * X_ev;
+        double k_h;
+        if ((X >= h.X0) && (X < h.Xmax))
+                k_h = hot_kinetic_of_grammage(h, X, hint);
+        else
+                k_h = cel_kinetic_energy(p, cfg.energy_loss, h.material, X);
+        HotVertex v;
+        v.k = energy - sgn * ratio * fabs(energy - k_h);
+        v.l.i = hint;
+        v.l.t = 0.;
+        v.located = hot_in_grid(h, v.k) ? 1 : 0;
+        if (v.located) v.l = hot_locate_K(h, v.k, hint);
+        return v;
+}
+
+/* General look-ups for energies off the grid (rare), out of line. */
+PB_NOINLINE double hot_cel_straggling(
+    const Physics & p, int material, double kinetic)
+{
+        return cel_straggling(p, material, kinetic);
+}
+
+PB_NOINLINE double hot_cel_energy_loss(
+    const Physics & p, int scheme, int material, double kinetic)
+{
+        return cel_energy_loss(p, scheme, material, kinetic);
+}
+
+PB_NOINLINE double hot_table_invlb1(
+    const Physics & p, int scheme, int material, double kinetic)
+{
+        double mu0, v;
+        table_get_msc(p, scheme, material, kinetic, &mu0, &v);
+        return v;
 }
 
 PB_NOINLINE double hot_del_cross_section(
@@ -465,18 +507,77 @@ PB_NOINLINE double hot_coulomb_ehs_length(
         return coulomb_ehs_length(p, material, kinetic);
 }
 
-/* A random stream reading the slot's Box-Muller cache: step_randn,
- * pumas.c:7016-7029. */
-template <class Rng>
+/* The random stream of the lean step (`Rng`): besides uniform(), which may
+ * generate a block when its buffer is empty,
+ *   uniform_fast(), log_uniform_fast()   no check: the caller of hot_step
+ *       guarantees 8 buffered variates, what a step draws outside its retry
+ *       loops;
+ *   uniform_keep(), log_uniform_keep()   for the retry loops: refill so that 8
+ *       stay buffered.
+ * log_uniform*() return the logarithm of the next variate (pb_hot_math.h on
+ * the GPU, the host libm on the CPU). */
+
+/* step_randn, pumas.c:7016-7029, on the slot's Box-Muller cache. */
+template <bool KEEP, class Rng>
 PB_FN double hot_randn(Rng & rng, uint32_t & flags, double & randn_next)
 {
         flags ^= HFL_RANDN;
         if (!(flags & HFL_RANDN)) return randn_next;
-        const double r = sqrt(-2. * xlog(rng.uniform()));
-        const double phi = 2. * PI * rng.uniform();
-        const SinCos sc = xsincos(phi);
+        const double r = hot_sqrt(
+            -2. * (KEEP ? rng.log_uniform_keep() : rng.log_uniform_fast()));
+        /* sin, cos of 2 pi u */
+        const SinCos sc = hot_sincospi(
+            2. * (KEEP ? rng.uniform_keep() : rng.uniform_fast()));
         randn_next = r * sc.c;
         return r * sc.s;
+}
+
+/* The general restatement of the step on the unpacked track (rare). */
+template <class Cfg, class S, class Rng>
+PB_NOINLINE int hot_step_general(const Physics & p, const Cfg & cfg,
+    const UniformGeometry & geo, const HotCtx & h, S & s, Rng & rng)
+{
+        State st;
+        Track t;
+        Loop l;
+        hot_unpack(s, p, cfg, geo, st, t, l);
+        t.step_X_limit = h.step_X_limit;
+        const int phase = stepping_step(p, cfg, geo, t, rng, st, l);
+        hot_pack(s, st, t, l, phase, false, 0.);
+        return phase;
+}
+
+/* A proper time limit reached inside a step, pumas.c:6762-6797 (uniform
+ * density). Out of line: only met with PUMAS_EVENT_LIMIT_TIME. */
+struct HotTimeLimit {
+        double step, k1, grammage;
+};
+PB_NOINLINE HotTimeLimit hot_time_limit(double momentum, double p_f, double sf1,
+    double time_max, double ti, double mass, double density, double grammage0,
+    double dX)
+{
+        HotTimeLimit r;
+        const double a = (momentum / p_f - 1.) / sf1;
+        const double c = -2. * (time_max - ti) * momentum / mass;
+        double step;
+        if (a != 0.) {
+                double delta = 1. - a * c;
+                if (delta < 0.) delta = 0.;
+                step = 1. / a * (sqrt(delta) - 1.);
+        } else {
+                step = -0.5 * c;
+        }
+        if (step < 0.) step = 0.;
+        const double p1 = momentum / (1 + a * step);
+        double k1 = sqrt(p1 * p1 - mass * mass) - mass;
+        if (k1 < 0.) k1 = 0.;
+        const double Xf = grammage0 + dX;
+        double grammage = grammage0 + step * density;
+        if (grammage > Xf) grammage = Xf;
+        r.step = step;
+        r.k1 = k1;
+        r.grammage = grammage;
+        return r;
 }
 
 /*
@@ -513,18 +614,18 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                         l0.t = s.ld(HF_T0);
                 else
                         l0 = hot_locate_K(h, e0, l0.i);
-                const double * const r0 = hot_K(h, l0);
+                const HotPtr r0 = hot_K(h, l0);
                 Xtot = hot_pchip(r0 + HK_X, l0.t); /* pumas.c:6318 */
 
                 /* local step length, pumas.c:6324-6347, 6386-6395 */
                 double step_loc = cfg.accuracy * h.density_i * Xtot;
                 if (mixed) {
                         if (flags & HFL_FIRST)
-                                invlb1 = hot_pchip(r0 + HK_MS1, l0.t) *
-                                    h.density;
+                                invlb1 =
+                                    hot_msc_invlb1(h, l0, e0) * h.density;
                         else
                                 invlb1 = s.ld(HF_INVLB1);
-                        const double stepT = cfg.accuracy / invlb1;
+                        const double stepT = hot_div(cfg.accuracy, invlb1);
                         if (stepT < step_loc) step_loc = stepT;
                 }
                 if (step_loc < STEP_MIN) step_loc = STEP_MIN;
@@ -539,23 +640,13 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                 }
                 dX = 0.5 * step * (h.density + h.density); /* pumas.c:6518 */
                 Xend = Xtot - sgn * dX;
-                lean = (Xend >= h.X0) && (Xend < h.Xmax);
+                lean = (Xend < h.Xmax);
         }
-        if (!lean) {
-                /* general restatement on the unpacked track */
-                State st;
-                Track t;
-                Loop l;
-                hot_unpack(s, p, cfg, geo, st, t, l);
-                t.step_X_limit = h.step_X_limit;
-                const int phase = stepping_step(p, cfg, geo, t, rng, st, l);
-                hot_pack(s, st, t, l, phase, false, 0.);
-                return phase;
-        }
+        if (!lean) return hot_step_general(p, cfg, geo, h, s, rng);
 
         /* ---- the lean step ------------------------------------------------ */
         flags &= ~HFL_FIRST;
-        const double momentum = sqrt(e0 * (e0 + 2. * h.mass));
+        const double momentum = hot_sqrt(e0 * (e0 + 2. * h.mass));
 
         /* position, pumas.c:6410-6414 */
         {
@@ -567,25 +658,29 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
 
         /* straggled end of step energy: step_fluctuate, pumas.c:6943-7005 */
         double k1, ratio = 0.;
-        const double * const r0 = hot_K(h, l0);
+        const HotPtr r0 = hot_K(h, l0);
         HLoc l1 = { 0, 0. }; /* the located end energy, when `have_l1` */
         bool have_l1 = false;
         {
-                k1 = hot_kinetic_of_grammage(h, Xend, l0.i);
+                /* (below the column: 0, pumas.c:3765) */
+                k1 = (Xend >= h.X0) ?
+                    hot_kinetic_of_grammage(h, Xend, l0.i) :
+                    0.;
                 const double dk0 = fabs(e0 - k1);
                 if ((k1 > 0.) && (dk0 > 0.)) {
                         double Omega1, de1 = 0.;
-                        const double tmp = dX / Xtot;
+                        const double tmp = hot_div(dX, Xtot);
                         if ((k1 >= h.K0) && (k1 < h.Kmax)) {
                                 const HLoc lc = hot_locate_K(h, k1, l0.i);
-                                const double * const rc = hot_K(h, lc);
+                                const HotPtr rc = hot_K(h, lc);
                                 Omega1 = hot_pchip(rc + HK_OMEGA, lc.t);
                                 if (tmp > 5E-02)
                                         de1 = hot_pchip(rc + HK_DE, lc.t);
                         } else {
-                                Omega1 = cel_straggling(p, h.material, k1);
+                                Omega1 =
+                                    hot_cel_straggling(p, h.material, k1);
                                 if (tmp > 5E-02)
-                                        de1 = cel_energy_loss(p,
+                                        de1 = hot_cel_energy_loss(p,
                                             cfg.energy_loss, h.material, k1);
                         }
                         const double Omega0 = hot_pchip(r0 + HK_OMEGA, l0.t);
@@ -593,38 +688,40 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                         if (tmp > 5E-02) {
                                 const double de0 =
                                     hot_pchip(r0 + HK_DE, l0.t);
-                                dk12 *= 1. + sgn * dX / dk0 * (de1 - de0);
+                                dk12 *= 1. +
+                                    hot_div(sgn * dX, dk0) * (de1 - de0);
                         }
-                        const double dk1 = sqrt(dk12);
+                        const double dk1 = hot_sqrt(dk12);
                         if (dk0 >= 3. * dk1) {
                                 double randn_next = s.ld(HF_RANDN);
-                                double u;
-                                do
-                                        u = hot_randn(rng, flags, randn_next);
-                                while (fabs(u) > 3.);
+                                double u =
+                                    hot_randn<false>(rng, flags, randn_next);
+                                while (fabs(u) > 3.)
+                                        u = hot_randn<true>(
+                                            rng, flags, randn_next);
                                 s.st(HF_RANDN, randn_next);
                                 u /= 1.015387;
                                 k1 += u * dk1;
                         } else if (dk0 >= 1.7320508 * dk1) {
                                 const double u =
-                                    1.7320508 * (1. - 2. * rng.uniform());
+                                    1.7320508 * (1. - 2. * rng.uniform_fast());
                                 k1 += u * dk1;
                         } else {
                                 const double dk32 = 3. * dk12;
                                 const double dk02 = dk0 * dk0;
                                 const double a =
-                                    1. - (dk32 - dk02) / (dk32 + 3. * dk02);
-                                if (rng.uniform() <= a) {
+                                    1. - hot_div(dk32 - dk02, dk32 + 3. * dk02);
+                                if (rng.uniform_fast() <= a) {
                                         const double b =
-                                            0.5 * (dk32 + 3. * dk02) / dk0;
-                                        const double u = rng.uniform();
+                                            hot_div(0.5 * (dk32 + 3. * dk02), dk0);
+                                        const double u = rng.uniform_fast();
                                         k1 = e0 - sgn * b * u;
                                         if (k1 < 0.) k1 = 0.;
                                 } else {
                                         k1 = e0;
                                 }
                         }
-                        ratio = fabs(e0 - k1) / dk0;
+                        ratio = hot_div(fabs(e0 - k1), dk0);
                 }
                 if (ratio == 0.) ratio = 1.;
         }
@@ -648,7 +745,7 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                 }
                 if (kinetic_limit >= 0.) {
                         const double grammage = grammage0 +
-                            fabs(e0 - kinetic_limit) / dk * dX;
+                            hot_div(fabs(e0 - kinetic_limit), dk) * dX;
                         k1 = kinetic_limit;
                         if ((grammage_max <= 0.) ||
                             (grammage < grammage_max)) {
@@ -679,16 +776,22 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                     hot_del_cross_section(p, h.material, k1);
                 if (tmp_del > xs_del) xs_del = tmp_del;
                 if (xs_del > 0.) {
-                        const double X_del = -xlog(rng.uniform()) / xs_del;
+                        const double X_del =
+                            hot_div(-rng.log_uniform_fast(), xs_del);
                         if (X_del < Xmax) {
-                                const double k_del = hot_vertex_energy(p, cfg,
-                                    h.material, e0, Xtot, X_del, ratio);
+                                const HotVertex v = hot_vertex(p, cfg, h, e0,
+                                    Xtot, X_del, ratio, l0.i);
+                                const double k_del = v.k;
                                 if (k_del > 0.) {
-                                        const double r =
-                                            hot_del_cross_section(
-                                                p, h.material, k_del) /
-                                            xs_del;
-                                        if (!(rng.uniform() > r)) {
+                                        const double r = hot_div(
+                                            v.located ?
+                                                hot_pchip(
+                                                    hot_K(h, v.l) + HK_CS,
+                                                    v.l.t) :
+                                                hot_del_cross_section(
+                                                    p, h.material, k_del),
+                                            xs_del);
+                                        if (!(rng.uniform_fast() > r)) {
                                                 k_x = k_del;
                                                 Xmax = X_del;
                                                 event = EVENT_VERTEX_DEL;
@@ -712,22 +815,27 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                 double lb_ehs;
                 if (kmin == e0)
                         lb_ehs = hot_ehs_length(h, l0, kmin);
-                else if (have_l1 && (kmin >= h.K1))
+                else if (have_l1)
                         lb_ehs = hot_ehs_length(h, l1, kmin);
                 else
                         lb_ehs = hot_coulomb_ehs_length(p, h.material, kmin);
                 if (lb_ehs > 0.) {
-                        const double X_ehs = -xlog(rng.uniform()) * lb_ehs;
+                        const double X_ehs = -rng.log_uniform_fast() * lb_ehs;
                         if (X_ehs < Xmax) {
-                                const double k_ehs = hot_vertex_energy(p, cfg,
-                                    h.material, e0, Xtot, X_ehs, ratio);
+                                const HotVertex v = hot_vertex(p, cfg, h, e0,
+                                    Xtot, X_ehs, ratio, l0.i);
+                                const double k_ehs = v.k;
                                 if (k_ehs > 0.) {
-                                        const double r =
-                                            hot_coulomb_ehs_length(
-                                                p, h.material, k_ehs) /
-                                            lb_ehs;
+                                        const double r = hot_div(
+                                            v.located ?
+                                                hot_ehs_length(
+                                                    h, v.l, k_ehs) :
+                                                hot_coulomb_ehs_length(
+                                                    p, h.material, k_ehs),
+                                            lb_ehs);
                                         if (!((r <= 0.) ||
-                                                (rng.uniform() > 1. / r))) {
+                                                (rng.uniform_fast() >
+                                                    hot_div(1., r)))) {
                                                 k_x = k_ehs;
                                                 Xmax = X_ehs;
                                                 event = EVENT_VERTEX_COULOMB;
@@ -752,7 +860,9 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                 if (!(event & EVENT_LIMIT_ENERGY)) {
                         if (!(event &
                                 (EVENT_VERTEX_COULOMB | EVENT_VERTEX_DEL))) {
-                                k1 = e0 - sgn * (grammage - grammage0) * dk / dX;
+                                k1 = e0 -
+                                    hot_div(sgn * (grammage - grammage0) * dk,
+                                        dX);
                                 if (k1 < 0.) k1 = 0.;
                                 event = EVENT_LIMIT_GRAMMAGE;
                                 have_l1 = false;
@@ -770,31 +880,22 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
         const double sf1 = step;
         {
                 const double p_f =
-                    (k1 <= 0) ? momentum : sqrt(k1 * (k1 + 2. * h.mass));
+                    (k1 <= 0) ? momentum : hot_sqrt(k1 * (k1 + 2. * h.mass));
                 const double ti = s.ld(HF_TIME);
                 double time =
-                    ti + 0.5 * step * h.mass * (1. / momentum + 1. / p_f);
+                    ti +
+                    0.5 * step * h.mass *
+                        (hot_div(1., momentum) + hot_div(1., p_f));
                 if ((time_max > 0.) && (time >= time_max)) {
                         event = EVENT_LIMIT_TIME;
                         time = time_max;
-                        const double a = (momentum / p_f - 1.) / sf1;
-                        const double c =
-                            -2. * (time_max - ti) * momentum / h.mass;
-                        if (a != 0.) {
-                                double delta = 1. - a * c;
-                                if (delta < 0.) delta = 0.;
-                                step = 1. / a * (sqrt(delta) - 1.);
-                        } else {
-                                step = -0.5 * c;
-                        }
-                        if (step < 0.) step = 0.;
-                        const double p1 = momentum / (1 + a * step);
-                        k1 = sqrt(p1 * p1 - h.mass * h.mass) - h.mass;
-                        if (k1 < 0.) k1 = 0.;
+                        const HotTimeLimit tl = hot_time_limit(momentum, p_f,
+                            sf1, time_max, ti, h.mass, h.density, grammage0,
+                            dX);
+                        step = tl.step;
+                        k1 = tl.k1;
+                        grammage = tl.grammage;
                         have_l1 = false;
-                        const double Xf = grammage0 + dX;
-                        grammage = grammage0 + step * h.density;
-                        if (grammage > Xf) grammage = Xf;
 
                         const double b = (step - sf1) * sgn;
                         s.st(HF_PX, s.ld(HF_PX) + b * s.ld(HF_UX));
@@ -819,14 +920,13 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                                 l1 = hot_locate_K(h, k1, l0.i);
                                 have_l1 = true;
                         }
-                        if (have_l1 && (k1 >= h.K1)) {
-                                invlb1_end = h.density *
-                                    hot_pchip(hot_K(h, l1) + HK_MS1, l1.t);
+                        if (have_l1) {
+                                invlb1_end =
+                                    h.density * hot_msc_invlb1(h, l1, k1);
                         } else {
-                                double mu0, v;
-                                table_get_msc(p, cfg.energy_loss, h.material,
-                                    k1, &mu0, &v);
-                                invlb1_end = h.density * v;
+                                invlb1_end = h.density *
+                                    hot_table_invlb1(p, cfg.energy_loss,
+                                        h.material, k1);
                         }
                 }
                 s.st(HF_INVLB1, invlb1_end);
@@ -846,15 +946,13 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
         if (mixed && ((invlb1 > 0.) || (invlb1_end > 0.))) {
                 double ilb1 = 0.25 * step * (invlb1 + invlb1_end);
                 if (ilb1 > 1.) ilb1 = 1.;
-                double mu;
-                do {
-                        mu = -ilb1 * xlog(rng.uniform());
-                } while (mu > 1.);
+                double mu = -ilb1 * rng.log_uniform_fast();
+                while (mu > 1.) mu = -ilb1 * rng.log_uniform_keep();
                 /* step_rotate_direction, pumas.c:7042-7095 */
                 const double cos_theta = 1 - 2 * mu;
                 const double stsq = 4 * mu * (1. - mu);
                 if (stsq > 0.) {
-                        const double st = sqrt(stsq);
+                        const double st = hot_sqrt(stsq);
                         const double d0 = s.ld(HF_UX), d1 = s.ld(HF_UY),
                                      d2 = s.ld(HF_UZ);
                         const double a0 = fabs(d0), a1 = fabs(d1),
@@ -863,7 +961,8 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                         const bool case_xy = !(a0 > a1) && (a1 > a2);
                         const double pa = (case_xz || case_xy) ? d0 : d1;
                         const double pb_ = case_xy ? d1 : d2;
-                        const double nrm = 1. / sqrt(pa * pa + pb_ * pb_);
+                        const double nrm =
+                            hot_div(1., hot_sqrt(pa * pa + pb_ * pb_));
                         const double u0x = case_xz ? -d2 * nrm :
                             (case_xy ? d1 * nrm : 0.);
                         const double u0y = case_xz ? 0. :
@@ -873,8 +972,9 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
                         const double u1x = u0y * d2 - u0z * d1;
                         const double u1y = u0z * d0 - u0x * d2;
                         const double u1z = u0x * d1 - u0y * d0;
-                        const double phi = PI * (1. - 2. * rng.uniform());
-                        const SinCos sc = xsincos(phi);
+                        /* sin, cos of phi = pi (1 - 2 u) */
+                        const SinCos sc =
+                            hot_sincospi(1. - 2. * rng.uniform_fast());
                         s.st(HF_UX,
                             cos_theta * d0 + st * (sc.c * u0x + sc.s * u1x));
                         s.st(HF_UY,
@@ -890,13 +990,13 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
         if (event != EVENT_NONE) {
                 /* weights, pumas.c:5309-5321 */
                 const double wt = xexp(
-                    -fabs(s.ld(HF_TIME) - s.ld(HF_TI)) / h.ctau);
+                    hot_div(-fabs(s.ld(HF_TIME) - s.ld(HF_TI)), h.ctau));
                 if (!forward) {
                         double de;
                         if (have_l1)
                                 de = hot_pchip(hot_K(h, l1) + HK_DE, l1.t);
                         else
-                                de = cel_energy_loss(
+                                de = hot_cel_energy_loss(
                                     p, cfg.energy_loss, h.material, k1);
                         s.st(HF_WEIGHT, s.ld(HF_WI) * wt * s.ld(HF_DEI) * de);
                 } else {
@@ -929,6 +1029,109 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
             ((uint32_t)phase << HFL_PHASE_SHIFT);
         s.stu(HF_FLAGS,
             (unsigned long long)flags | ((unsigned long long)n_steps << 32));
+        return phase;
+}
+
+/* The general restatement of a hard elastic event on the unpacked track. */
+template <class Cfg, class S, class Rng>
+PB_NOINLINE int hot_ehs_general(const Physics & p, const Cfg & cfg,
+    const UniformGeometry & geo, const HotCtx & h, S & s, Rng & rng)
+{
+        State st;
+        Track t;
+        Loop l;
+        hot_unpack(s, p, cfg, geo, st, t, l);
+        t.step_X_limit = h.step_X_limit;
+        const int phase = stepping_ehs(p, cfg, geo, t, rng, st, l);
+        hot_pack(s, st, t, l, phase, false, 0.);
+        return phase;
+}
+
+/*
+ * A hard elastic event of a track in PHASE_EHS: transport_do_ehs
+ * (pumas.c:5768-5885), then the stop check and the re-arming of the stepping
+ * loop (pumas.c:5398-5402, 5476-5488 and transport_limit, pumas.c:5569-5631).
+ * Only the energy and the direction of the track take part in the event; the
+ * rest of the slot is touched by the re-arming alone.
+ */
+template <class Cfg, class S, class Rng>
+PB_NOINLINE int hot_ehs(const Physics & p, const Cfg & cfg,
+    const UniformGeometry & geo, const HotCtx & h, S & s, Rng & rng)
+{
+        constexpr bool forward = (Cfg::direction == MODE_FORWARD);
+        const double kinetic = s.ld(HF_ENERGY);
+        if (!hot_in_grid(h, kinetic))
+                return hot_ehs_general(p, cfg, geo, h, s, rng);
+
+        const unsigned long long fw = s.ldu(HF_FLAGS);
+        uint32_t flags = (uint32_t)fw;
+        State st;
+        st.energy = kinetic;
+        st.direction[0] = s.ld(HF_UX);
+        st.direction[1] = s.ld(HF_UY);
+        st.direction[2] = s.ld(HF_UZ);
+        transport_do_ehs(p, cfg, rng, st, h.material,
+            (int)((flags >> HFL_IK_SHIFT) & 0xffu));
+        s.st(HF_UX, st.direction[0]);
+        s.st(HF_UY, st.direction[1]);
+        s.st(HF_UZ, st.direction[2]);
+
+        int event = (int)(flags & HFL_EVENT_MASK);
+        int phase = PHASE_STEP;
+        if (cfg.event & event) {
+                phase = PHASE_DONE; /* (stepping_finish below) */
+        } else {
+                /* re-arm: pumas.c:5476-5488 */
+                const double weight = s.ld(HF_WEIGHT);
+                s.st(HF_TI, s.ld(HF_TIME));
+                s.st(HF_WI, weight);
+                if (!forward) {
+                        /* (Xf and dei only enter the backward weights) */
+                        HLoc l;
+                        l.i = (int)((flags >> HFL_IK_SHIFT) & 0xffu);
+                        if (flags & HFL_LOCATED)
+                                l.t = s.ld(HF_T0);
+                        else
+                                l = hot_locate_K(h, kinetic, l.i);
+                        const HotPtr r = hot_K(h, l);
+                        s.st(HF_XF, hot_pchip(r + HK_X, l.t));
+                        s.st(HF_DEI, 1. / hot_pchip(r + HK_DE, l.t));
+                }
+                /* transport_limit in the straggled mode */
+                event = EVENT_NONE;
+                if (weight <= 0.) {
+                        event = EVENT_WEIGHT;
+                } else if (forward) {
+                        const double kinetic_min =
+                            (cfg.event & EVENT_LIMIT_ENERGY) ?
+                            cfg.limit_energy :
+                            0.;
+                        if (kinetic <= kinetic_min) event = EVENT_LIMIT_ENERGY;
+                } else if ((cfg.event & EVENT_LIMIT_ENERGY) &&
+                    (kinetic >= cfg.limit_energy)) {
+                        event = EVENT_LIMIT_ENERGY;
+                }
+                if (event != EVENT_NONE) phase = PHASE_DONE;
+        }
+        if (phase == PHASE_DONE) {
+                /* stepping_finish, pumas.c:5492-5513 */
+                if (forward) {
+                        const double kinetic_min =
+                            (cfg.event & EVENT_LIMIT_ENERGY) ?
+                            cfg.limit_energy :
+                            0.;
+                        if (fabs(kinetic - kinetic_min) < (double)FLT_EPSILON)
+                                s.st(HF_ENERGY, kinetic_min);
+                } else if ((cfg.event & EVENT_LIMIT_ENERGY) &&
+                    (fabs(kinetic - cfg.limit_energy) < (double)FLT_EPSILON)) {
+                        s.st(HF_ENERGY, cfg.limit_energy);
+                }
+        }
+        flags = (flags & ~(HFL_EVENT_MASK | HFL_PHASE_MASK)) |
+            ((uint32_t)event & HFL_EVENT_MASK) |
+            ((uint32_t)phase << HFL_PHASE_SHIFT);
+        s.stu(HF_FLAGS,
+            (unsigned long long)flags | (fw & 0xffffffff00000000ull));
         return phase;
 }
 

@@ -109,6 +109,12 @@ struct Physics {
         const int * comp_element;
         const double * comp_fraction;
         const Element * element;
+
+        /* The tables of a Monte Carlo step re-packed per grid cell
+         * (pb_hot_tables.h): [material][cell][HOTK_WORDS] and
+         * [material][cell][HOTX_WORDS]. */
+        const double * hotK;
+        const double * hotX;
 };
 
 /* ---- table accessors, pumas.c:4260-4752 -------------------------------- */
