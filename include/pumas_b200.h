@@ -519,6 +519,54 @@ PUMAS_API enum pumas_return pumas_b200_tally(const struct pumas_state * states,
     double energy_max, int n_bins, double * out, void * scratch,
     void * cuda_stream);
 
+/* New. pumas_context_transport_n without the wait: the batch is enqueued on
+ * the context's stream and the call returns. `states`, `events`, `media` must
+ * be device pointers. pumas_b200_context_synchronize waits for every batch
+ * enqueued since the last wait and raises the first error one of their tracks
+ * met (the return code pumas_context_transport_n would have given). */
+PUMAS_API enum pumas_return pumas_b200_context_transport_async(
+    struct pumas_context * context, long n, struct pumas_state * states,
+    int * events, int * media);
+PUMAS_API enum pumas_return pumas_b200_context_synchronize(
+    struct pumas_context * context);
+
+/* New: multi-GPU runs (one rank per GPU, tracks sharded by id range with
+ * pumas_b200_context_track_offset_set). The tallies of
+ * the batches of a rank are accumulated on the device
+ * (pumas_b200_tally_accumulate: total[k] += batch[k], in launch order) and
+ * summed over the ranks ONCE, at the end, by pumas_b200_comm_allreduce
+ * (ncclAllReduce of doubles, in place, on `cuda_stream`). The communicator is
+ * created from a unique id made on one rank and handed to the others by the
+ * caller (MPI, a file, torch.distributed ...), or wraps the caller's own
+ * ncclComm_t. NCCL is loaded at run time (libnccl.so.2, or the library named
+ * by the environment variable PUMAS_B200_NCCL); without it these calls return
+ * PUMAS_RETURN_VALUE_ERROR and pumas_b200_comm_available() is 0. */
+struct pumas_b200_comm;
+#define PUMAS_B200_UNIQUE_ID_BYTES 128
+PUMAS_API int pumas_b200_comm_available(void);
+PUMAS_API enum pumas_return pumas_b200_comm_unique_id(void * id, int bytes);
+PUMAS_API enum pumas_return pumas_b200_comm_create(
+    struct pumas_b200_comm ** comm, int rank, int world, const void * id,
+    int bytes);
+PUMAS_API enum pumas_return pumas_b200_comm_wrap(
+    struct pumas_b200_comm ** comm, void * nccl_comm, int rank, int world);
+PUMAS_API enum pumas_return pumas_b200_comm_allreduce(
+    struct pumas_b200_comm * comm, double * values, long count,
+    void * cuda_stream);
+PUMAS_API void pumas_b200_comm_destroy(struct pumas_b200_comm ** comm);
+PUMAS_API enum pumas_return pumas_b200_tally_accumulate(
+    double * total, const double * batch, long count, void * cuda_stream);
+
+/* New: tally over a grid of bins (examples/pumas/geometry.c extended to a
+ * zenith x azimuth grid, BASELINE.json configs[3]): the batch holds `per_bin`
+ * consecutive tracks per bin; out[3 b .. 3 b + 2] (device) receives the sum of
+ * the weights, of their squares and the number of the tracks of bin b whose
+ * end event intersects `event_mask` (0 = all). Fixed reduction order. Ranks
+ * shard the grid by bin and by track id and all-reduce `out`. */
+PUMAS_API enum pumas_return pumas_b200_tally_segments(
+    const struct pumas_state * states, const int * events, long n_bins,
+    long per_bin, int event_mask, double * out, void * cuda_stream);
+
 /* New: measured FP64 FMA throughput of the current device, in TFLOP/s (the
  * denominator of the roofline fraction reported by bench.py). */
 PUMAS_API enum pumas_return pumas_b200_fp64_peak(double * tflops);

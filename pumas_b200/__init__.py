@@ -210,6 +210,22 @@ def library():
         ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p]
     lib.pumas_b200_fp64_peak.argtypes = [c_double_p]
+    lib.pumas_b200_context_transport_async.argtypes = [
+        ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p]
+    lib.pumas_b200_context_synchronize.argtypes = [ctypes.c_void_p]
+    lib.pumas_b200_tally_accumulate.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+    lib.pumas_b200_tally_segments.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_long,
+        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    lib.pumas_b200_comm_unique_id.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.pumas_b200_comm_create.argtypes = [
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, ctypes.c_int,
+        ctypes.c_void_p, ctypes.c_int]
+    lib.pumas_b200_comm_allreduce.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p]
+    lib.pumas_b200_comm_destroy.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
     lib.pumas_error_handler_set.argtypes = [_HANDLER_T]
     lib.pumas_error_handler_set(_handler)
     _lib = lib
@@ -244,6 +260,59 @@ def tally(states_ptr, events_ptr, n, event_mask, energy_min, energy_max,
         ctypes.c_void_p(states_ptr), ctypes.c_void_p(events_ptr), n,
         event_mask, energy_min, energy_max, n_bins, ctypes.c_void_p(out_ptr),
         ctypes.c_void_p(scratch_ptr), ctypes.c_void_p(stream)))
+
+
+def tally_accumulate(total_ptr, batch_ptr, count, stream=0):
+    """total[k] += batch[k] on the device (device pointers as integers)."""
+    _check(library().pumas_b200_tally_accumulate(
+        ctypes.c_void_p(total_ptr), ctypes.c_void_p(batch_ptr), count,
+        ctypes.c_void_p(stream)))
+
+
+def tally_segments(states_ptr, events_ptr, n_bins, per_bin, event_mask,
+                   out_ptr, stream=0):
+    """pumas_b200_tally_segments on device pointers (integers)."""
+    _check(library().pumas_b200_tally_segments(
+        ctypes.c_void_p(states_ptr), ctypes.c_void_p(events_ptr), n_bins,
+        per_bin, event_mask, ctypes.c_void_p(out_ptr),
+        ctypes.c_void_p(stream)))
+
+
+class Comm:
+    """The library's NCCL communicator (pumas_b200_comm_*): one rank per GPU.
+    `exchange(bytes_or_None) -> bytes` hands the unique id made on rank 0 to
+    every rank (e.g. a torch.distributed / MPI broadcast)."""
+
+    def __init__(self, rank, world, exchange):
+        lib = library()
+        if not lib.pumas_b200_comm_available():
+            raise RuntimeError("NCCL (libnccl.so.2) could not be loaded")
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            _check(lib.pumas_b200_comm_unique_id(buf, 128))
+        uid = exchange(bytes(buf.raw) if rank == 0 else None)
+        buf = ctypes.create_string_buffer(bytes(uid), 128)
+        self._ptr = ctypes.c_void_p()
+        _check(lib.pumas_b200_comm_create(
+            ctypes.byref(self._ptr), rank, world, buf, 128))
+        self.rank, self.world = rank, world
+
+    def allreduce(self, values_ptr, count, stream=0):
+        """Sum `count` doubles at the device pointer over the ranks, in
+        place, on `stream`."""
+        _check(library().pumas_b200_comm_allreduce(
+            self._ptr, ctypes.c_void_p(values_ptr), count,
+            ctypes.c_void_p(stream)))
+
+    def close(self):
+        if self._ptr:
+            library().pumas_b200_comm_destroy(ctypes.byref(self._ptr))
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 _libc = ctypes.CDLL(None)
@@ -378,6 +447,18 @@ class Context:
         _check(library().pumas_context_transport_n(
             self._ptr, n, ctypes.c_void_p(states_ptr),
             ctypes.c_void_p(events_ptr), ctypes.c_void_p(media_ptr)))
+
+    def transport_async(self, n, states_ptr, events_ptr=None, media_ptr=None):
+        """pumas_b200_context_transport_async: enqueue a batch (device
+        pointers) on the context's stream and return."""
+        _check(library().pumas_b200_context_transport_async(
+            self._ptr, n, ctypes.c_void_p(states_ptr),
+            ctypes.c_void_p(events_ptr), ctypes.c_void_p(media_ptr)))
+
+    def synchronize(self):
+        """Wait for the batches enqueued by transport_async; raises the first
+        error one of their tracks met."""
+        _check(library().pumas_b200_context_synchronize(self._ptr))
 
     def last_counters(self, n):
         nrand = np.zeros(n, dtype=np.uint32)

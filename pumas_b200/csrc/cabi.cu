@@ -28,13 +28,19 @@
 #include "pumas_b200.h"
 
 /* ---- opaque objects ------------------------------------------------------ */
-struct pumas_physics {
-        pb::HostPhysics host;
-        /* Device copy of host.image, created on first use. */
-        std::mutex mutex;
+/* A copy of the tables on one device. */
+struct DeviceImage {
         int device;
         void * d_image;
         pb::Physics d_view;
+};
+
+struct pumas_physics {
+        pb::HostPhysics host;
+        /* Device copies of host.image, one per device, created on first use
+         * (a host process may drive several GPUs with one physics object). */
+        std::mutex mutex;
+        std::vector<DeviceImage> images;
 };
 
 namespace {
@@ -65,6 +71,8 @@ struct ContextImpl {
         int last_launches;
         cudaEvent_t ev0, ev1;
         int events_ready;
+        int device;  /* the device the buffers live on, -1: none yet */
+        int pending; /* batches enqueued by transport_async, not waited for */
         int extra_memory;
         /* user memory follows */
         double data[1];
@@ -158,33 +166,35 @@ int device_usable(std::string * why)
         return 1;
 }
 
-enum pumas_return physics_upload(
-    pumas_function_t * caller, pumas_physics * physics)
+enum pumas_return physics_upload(pumas_function_t * caller,
+    pumas_physics * physics, pb::Physics * d_view)
 {
         std::lock_guard<std::mutex> lock(physics->mutex);
         int dev = 0;
         cudaGetDevice(&dev);
-        if ((physics->d_image != nullptr) && (physics->device == dev))
-                return PUMAS_RETURN_SUCCESS;
-        if (physics->d_image != nullptr) {
-                /* A physics object serves one device per process (one process
-                 * per GPU); re-home it if the device changed. */
-                cudaFree(physics->d_image);
-                physics->d_image = nullptr;
+        for (size_t i = 0; i < physics->images.size(); i++) {
+                if (physics->images[i].device == dev) {
+                        *d_view = physics->images[i].d_view;
+                        return PUMAS_RETURN_SUCCESS;
+                }
         }
+        DeviceImage image;
+        image.device = dev;
+        image.d_image = nullptr;
         const size_t size = physics->host.image.size();
-        cudaError_t e = cudaMalloc(&physics->d_image, size);
+        cudaError_t e = cudaMalloc(&image.d_image, size);
         if (e == cudaSuccess)
-                e = cudaMemcpy(physics->d_image, physics->host.image.data(),
-                    size, cudaMemcpyHostToDevice);
+                e = cudaMemcpy(image.d_image, physics->host.image.data(), size,
+                    cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
-                physics->d_image = nullptr;
+                if (image.d_image != nullptr) cudaFree(image.d_image);
                 return raise(caller, PUMAS_RETURN_MEMORY_ERROR, __FILE__,
                     __LINE__, "could not upload the physics tables (%s)",
                     cudaGetErrorString(e));
         }
-        physics->device = dev;
-        physics->d_view = physics->host.view_at(physics->d_image);
+        image.d_view = physics->host.view_at(image.d_image);
+        physics->images.push_back(image);
+        *d_view = image.d_view;
         return PUMAS_RETURN_SUCCESS;
 }
 
@@ -441,8 +451,6 @@ enum pumas_return pumas_physics_load(
         if (physics == nullptr)
                 return RAISE(pumas_physics_load, PUMAS_RETURN_MEMORY_ERROR,
                     "could not allocate memory");
-        physics->device = -1;
-        physics->d_image = nullptr;
         std::string err;
         const int rc = pb::load_physics_stream(stream, physics->host, err);
         if (rc != 0) {
@@ -495,7 +503,14 @@ void pumas_physics_destroy(struct pumas_physics ** physics_ptr)
 {
         if ((physics_ptr == nullptr) || (*physics_ptr == nullptr)) return;
         pumas_physics * physics = *physics_ptr;
-        if (physics->d_image != nullptr) cudaFree(physics->d_image);
+        for (size_t i = 0; i < physics->images.size(); i++) {
+                /* (freed on the device they were allocated on) */
+                int dev = 0;
+                cudaGetDevice(&dev);
+                cudaSetDevice(physics->images[i].device);
+                cudaFree(physics->images[i].d_image);
+                cudaSetDevice(dev);
+        }
         physics_delete(physics);
         *physics_ptr = nullptr;
 }
@@ -957,6 +972,7 @@ enum pumas_return pumas_context_create(struct pumas_context ** context_,
                     "could not allocate memory");
         memset(c, 0x0, size);
         c->physics = physics;
+        c->device = -1;
         c->extra_memory = extra_memory;
         c->api.user_data = (extra_memory > 0) ? c->data : nullptr;
         c->api.medium = nullptr;
@@ -1180,27 +1196,30 @@ enum pumas_return pumas_b200_context_stream_set(
 }
 
 /* ---- transport -------------------------------------------------------------- */
-enum pumas_return pumas_context_transport_n(struct pumas_context * context,
-    long n, struct pumas_state * states, int * events, int * media)
+namespace {
+
+/* One batch, for the public entry point `caller` (errors are attributed to
+ * it, as the reference does). `async`: enqueue on the context's stream and
+ * return; every pointer must then be a device pointer, and
+ * pumas_b200_context_synchronize collects the status. */
+enum pumas_return transport_batch(pumas_function_t * caller,
+    struct pumas_context * context, long n, struct pumas_state * states,
+    int * events, int * media, bool async)
 {
+#define RAISE_C(rc, ...) raise(caller, rc, __FILE__, __LINE__, __VA_ARGS__)
         if (context == nullptr)
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+                return RAISE_C(PUMAS_RETURN_VALUE_ERROR, "no context (null)");
         if ((states == nullptr) && (n > 0))
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_VALUE_ERROR, "no state (null)");
+                return RAISE_C(PUMAS_RETURN_VALUE_ERROR, "no state (null)");
         if (n < 0)
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_VALUE_ERROR, "negative number of states");
+                return RAISE_C(PUMAS_RETURN_VALUE_ERROR, "negative number of states");
         ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
         pumas_physics * physics = const_cast<pumas_physics *>(c->physics);
         if (physics == nullptr)
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_PHYSICS_ERROR,
+                return RAISE_C(PUMAS_RETURN_PHYSICS_ERROR,
                     "the Physics has not been initialised");
         if (!c->has_geometry)
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_MEDIUM_ERROR, "no medium specified");
+                return RAISE_C(PUMAS_RETURN_MEDIUM_ERROR, "no medium specified");
 
         /* Configuration checks, pumas.c:3152-3177. */
         const pb::Settings cfg = settings_from(context);
@@ -1208,38 +1227,45 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
         if ((hp.particle == PUMAS_PARTICLE_TAU) &&
             (cfg.direction == pb::MODE_FORWARD) &&
             (cfg.decay == pb::MODE_WEIGHTED))
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_DECAY_ERROR,
+                return RAISE_C(PUMAS_RETURN_DECAY_ERROR,
                     "`PUMAS_MODE_WEIGHTED' mode is not valid for forward taus");
         if ((cfg.accuracy <= 0) || (cfg.accuracy > 1))
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_ACCURACY_ERROR,
+                return RAISE_C(PUMAS_RETURN_ACCURACY_ERROR,
                     "bad accuracy value (expected a value in ]0,1], got %g)",
                     cfg.accuracy);
         if ((cfg.direction == pb::MODE_BACKWARD) &&
             (cfg.energy_loss > pb::MODE_CSDA) && (hp.cutoff < 1E-02))
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_ACCURACY_ERROR,
+                return RAISE_C(PUMAS_RETURN_ACCURACY_ERROR,
                     "bad cutoff value for backward transport (expected a "
                     "value greater than or equal to 0.01, got %g)",
                     hp.cutoff);
         if ((cfg.energy_loss < pb::MODE_DISABLED) ||
             (cfg.energy_loss > pb::MODE_STRAGGLED))
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_INDEX_ERROR,
+                return RAISE_C(PUMAS_RETURN_INDEX_ERROR,
                     "invalid energy loss scheme [%d]", cfg.energy_loss);
         c->last_n = 0;
         c->last_ms = 0.;
         c->last_launches = 0;
         if (n == 0) return PUMAS_RETURN_SUCCESS;
 
-        /* The device: there is no CPU path. */
+        /* The device: there is no CPU path. A context lives on the device
+         * that was current at its first batch. */
         std::string why;
         if (!device_usable(&why))
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_INTERNAL_ERROR, "%s", why.c_str());
-        enum pumas_return rc =
-            physics_upload(FN(pumas_context_transport_n), physics);
+                return RAISE_C(PUMAS_RETURN_INTERNAL_ERROR, "%s", why.c_str());
+        {
+                int dev = 0;
+                cudaGetDevice(&dev);
+                if (c->device < 0) c->device = dev;
+                if (c->device != dev)
+                        return RAISE_C(PUMAS_RETURN_INTERNAL_ERROR,
+                            "the context was first used on CUDA device %d, "
+                            "the current device is %d (one context per "
+                            "device)",
+                            c->device, dev);
+        }
+        pb::Physics d_view;
+        enum pumas_return rc = physics_upload(caller, physics, &d_view);
         if (rc != PUMAS_RETURN_SUCCESS) return rc;
 
         if (!c->seed_set) {
@@ -1249,13 +1275,18 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
 
         cudaError_t e = context_reserve(c, n);
         if (e != cudaSuccess)
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_MEMORY_ERROR,
+                return RAISE_C(PUMAS_RETURN_MEMORY_ERROR,
                     "could not allocate device memory (%s)",
                     cudaGetErrorString(e));
 
         const cudaStream_t stream = c->stream;
         const bool states_on_device = is_device_pointer(states);
+        if (async &&
+            (!states_on_device ||
+                ((events != nullptr) && !is_device_pointer(events)) ||
+                ((media != nullptr) && !is_device_pointer(media))))
+                return RAISE_C(PUMAS_RETURN_VALUE_ERROR,
+                    "asynchronous transport needs device pointers");
         const bool events_on_device =
             (events != nullptr) && is_device_pointer(events);
         const bool media_on_device =
@@ -1269,16 +1300,26 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
         if (!states_on_device)
                 e = cudaMemcpyAsync(d_states, states, n * sizeof(pb::State),
                     cudaMemcpyHostToDevice, stream);
-        if (e == cudaSuccess)
+        if ((e == cudaSuccess) && !c->pending)
                 e = cudaMemsetAsync(c->d_status, 0, sizeof(int), stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev0, stream);
         if (e == cudaSuccess)
-                e = pb::launch_transport(physics->d_view, physics->host.view, cfg,
+                e = pb::launch_transport(d_view, physics->host.view, cfg,
                     c->geometry,
                     (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_states,
                     d_events, d_media, c->d_status, c->d_random, c->d_steps,
                     c->d_workspace, c->kernel, stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev1, stream);
+        if (async) {
+                if (e != cudaSuccess)
+                        return RAISE_C(PUMAS_RETURN_INTERNAL_ERROR,
+                            "CUDA error (%s)", cudaGetErrorString(e));
+                c->pending = 1;
+                c->last_launches = pb::transport_last_launches();
+                c->last_n = n;
+                c->track_offset += (unsigned long long)n;
+                return PUMAS_RETURN_SUCCESS;
+        }
         int status = 0;
         if ((e == cudaSuccess) && !states_on_device)
                 e = cudaMemcpyAsync(states, d_states, n * sizeof(pb::State),
@@ -1294,8 +1335,7 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
                     cudaMemcpyDeviceToHost, stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
         if (e != cudaSuccess)
-                return RAISE(pumas_context_transport_n,
-                    PUMAS_RETURN_INTERNAL_ERROR, "CUDA error (%s)",
+                return RAISE_C(PUMAS_RETURN_INTERNAL_ERROR, "CUDA error (%s)",
                     cudaGetErrorString(e));
         float ms = 0.f;
         cudaEventElapsedTime(&ms, c->ev0, c->ev1);
@@ -1304,8 +1344,51 @@ enum pumas_return pumas_context_transport_n(struct pumas_context * context,
         c->last_n = n;
         c->track_offset += (unsigned long long)n;
 
+        c->pending = 0;
         if (status != 0)
-                return RAISE(pumas_context_transport_n,
+                return RAISE_C((enum pumas_return)status, "%s", return_text(status));
+        return PUMAS_RETURN_SUCCESS;
+#undef RAISE_C
+}
+
+} /* namespace */
+
+enum pumas_return pumas_context_transport_n(struct pumas_context * context,
+    long n, struct pumas_state * states, int * events, int * media)
+{
+        return transport_batch(FN(pumas_context_transport_n), context, n,
+            states, events, media, false);
+}
+
+enum pumas_return pumas_b200_context_transport_async(
+    struct pumas_context * context, long n, struct pumas_state * states,
+    int * events, int * media)
+{
+        return transport_batch(FN(pumas_b200_context_transport_async), context,
+            n, states, events, media, true);
+}
+
+enum pumas_return pumas_b200_context_synchronize(struct pumas_context * context)
+{
+        if (context == nullptr)
+                return RAISE(pumas_b200_context_synchronize,
+                    PUMAS_RETURN_VALUE_ERROR, "no context (null)");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        if (!c->pending) return PUMAS_RETURN_SUCCESS;
+        int status = 0;
+        cudaError_t e = cudaMemcpyAsync(&status, c->d_status, sizeof(int),
+            cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        c->pending = 0;
+        if (e != cudaSuccess)
+                return RAISE(pumas_b200_context_synchronize,
+                    PUMAS_RETURN_INTERNAL_ERROR, "CUDA error (%s)",
+                    cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->last_ms = ms; /* (the last batch of the series) */
+        if (status != 0)
+                return RAISE(pumas_b200_context_synchronize,
                     (enum pumas_return)status, "%s", return_text(status));
         return PUMAS_RETURN_SUCCESS;
 }
@@ -1322,8 +1405,8 @@ enum pumas_return pumas_context_transport(struct pumas_context * context,
                     "no state (null)");
         if (media != nullptr) media[0] = media[1] = nullptr;
         int e = PUMAS_EVENT_NONE;
-        const enum pumas_return rc =
-            pumas_context_transport_n(context, 1, state, &e, nullptr);
+        const enum pumas_return rc = transport_batch(
+            FN(pumas_context_transport), context, 1, state, &e, nullptr, false);
         if (event != nullptr) *event = (enum pumas_event)e;
         return rc;
 }

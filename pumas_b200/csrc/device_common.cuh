@@ -158,6 +158,23 @@ inline const Tunables & tunables()
         return t;
 }
 
+/* Per device facts (a host process may drive several GPUs). */
+constexpr int MAX_DEVICES = 64;
+inline int current_device()
+{
+        int dev = 0;
+        cudaGetDevice(&dev);
+        return ((dev >= 0) && (dev < MAX_DEVICES)) ? dev : 0;
+}
+inline int device_sms(int dev)
+{
+        static int sms[MAX_DEVICES] = { 0 };
+        if (sms[dev] == 0)
+                cudaDeviceGetAttribute(
+                    &sms[dev], cudaDevAttrMultiProcessorCount, dev);
+        return sms[dev];
+}
+
 /* Kernels launched by the last launch_transport of this process (diagnostics:
  * pumas_b200_context_last_kernel_time). */
 inline int & last_launch_count()

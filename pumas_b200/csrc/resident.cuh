@@ -1412,21 +1412,24 @@ cudaError_t launch_resident(const Physics & p, const Cfg & cfg, const Geo & geo,
     int * media, int * status, unsigned int * n_random, unsigned int * n_steps,
     void * workspace, cudaStream_t stream)
 {
-        static size_t ready = 0; /* per instantiation: opted-in size */
+        /* per instantiation and per device: the opted-in size */
+        static size_t ready[MAX_DEVICES] = { 0 };
         const Tunables & t = tunables();
         const size_t smem =
             resident_smem_bytes<RS_WARPS>(resident_pooled(cfg));
         cudaError_t e;
-        if (ready < smem) {
+        const int dev = current_device();
+        if (ready[dev] < smem) {
                 e = cudaFuncSetAttribute(transport_resident_kernel<Cfg, Geo>,
                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                ready = smem;
+                ready[dev] = smem;
         }
+        const int sms = device_sms(dev);
         /* Persistent grid: one CTA per SM, fewer for small n. */
         const long per_cta = 32L * RS_STEP_WARPS;
         const long want = (n + per_cta - 1) / per_cta;
-        int grid = (want < t.sms) ? (int)want : t.sms;
+        int grid = (want < sms) ? (int)want : sms;
         if ((t.grid_cap > 0) && (t.grid_cap < grid)) grid = t.grid_cap;
         /* Offload: one CTA in 15 serves the hard inelastic events of the
          * others (headline workload on B200: 8 to 16 of 148 give the same
@@ -1436,7 +1439,7 @@ cudaError_t launch_resident(const Physics & p, const Cfg & cfg, const Geo & geo,
                 n_del_ctas = (t.del_ctas > 0) ? t.del_ctas : (grid + 7) / 15;
                 if (n_del_ctas < 1) n_del_ctas = 1;
                 if (n_del_ctas > 16) n_del_ctas = 16;
-                if (grid + n_del_ctas > t.sms) grid = t.sms - n_del_ctas;
+                if (grid + n_del_ctas > sms) grid = sms - n_del_ctas;
                 if (grid < 1) return cudaErrorInvalidConfiguration;
         }
         unsigned long long * cursor =

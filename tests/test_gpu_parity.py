@@ -4,10 +4,13 @@ same seeded inputs and the same Philox streams.
 
 Criterion (BASELINE.json north_star): per-track final states agree within 1e-9
 relative in fp64; the fraction of tracks whose event sequence diverges (a
-different number of consumed variates or a different end event) is reported and
-must stay small, since the two sides use different libm implementations
-(glibc vs CUDA: <= 2 ulp apart) whose differences can flip a comparison
-against a random number.
+different number of consumed variates or a different end event) is bounded per
+workload, and so are the fraction of in-sync tracks above 1e-9 and their
+largest difference: by default NONE of either, with the measured exceptions
+listed at BOUNDS (the two sides use different libm implementations, <= 2 ulp
+apart, whose differences are amplified by ill-conditioned steps of the
+reference algorithm). profiles/tools/parity_report.py runs the same
+comparison and writes the numbers to profiles/parity_r2.json.
 """
 import numpy as np
 import pytest
@@ -19,35 +22,50 @@ from workloads import WORKLOADS
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-9
+# Tracks per workload (the reference runs them on the host cores in seconds).
 N_TRACKS = {
-    "headline": 3000, "rock_3km": 1500, "straight": 4000,
-    "straight_mixed": 4000, "csda_water": 20000, "csda_spectrum_fwd": 20000,
-    "csda_spectrum_bwd": 20000, "mixed_loss": 20000,
-    "mixed_loss_scattering": 2000, "mixed_loss_bwd": 4000,
-    "csda_magnet_fwd": 20000, "csda_magnet_bwd": 20000,
-    "models_kkb_fwd": 3000, "models_kkb_bwd": 3000, "models_abm_fwd": 3000,
-    "models_abm_bwd": 3000,
-    "geometry_detailed": 4000, "geometry_fast": 20000, "layers_check": 2000,
-    "decay_randomised": 2000, "no_loss": 1500, "tau_ice": 20000,
-    "above_grid": 4000, "above_grid_mixed": 20000, "vertex_stop": 20000, "vertex_stop_bwd": 20000, "limits_all": 6000,
-    "limits_all_bwd": 6000, "limits_all_csda": 6000,
-    "limits_all_mixed_bwd": 6000,
+    "headline": 100000, "rock_3km": 20000, "straight": 100000,
+    "straight_mixed": 50000, "csda_water": 200000,
+    "csda_spectrum_fwd": 100000, "csda_spectrum_bwd": 100000,
+    "mixed_loss": 100000, "mixed_loss_scattering": 20000,
+    "mixed_loss_bwd": 40000, "csda_magnet_fwd": 100000,
+    "csda_magnet_bwd": 100000, "models_kkb_fwd": 20000,
+    "models_kkb_bwd": 20000, "models_abm_fwd": 20000, "models_abm_bwd": 20000,
+    "geometry_detailed": 40000, "geometry_fast": 100000,
+    "layers_check": 20000, "decay_randomised": 20000, "no_loss": 10000,
+    "tau_ice": 100000, "above_grid": 20000, "above_grid_mixed": 100000,
+    "vertex_stop": 100000, "vertex_stop_bwd": 100000, "limits_all": 40000,
+    "limits_all_bwd": 40000, "limits_all_csda": 40000,
+    "limits_all_mixed_bwd": 40000,
 }
-# Largest tolerated fraction of tracks that do not meet RTOL: tracks whose
-# event sequence diverged (different number of variates or end event) plus
-# tracks that stayed in sync but went through an ill-conditioned operation of
-# the reference algorithm, where the <= 2 ulp differences between glibc and
-# CUDA libm are amplified beyond 1e-9: the single precision DCS interpolation
-# (pumas.c:11279-11346, one float ulp = 6e-8) and the inversion of the number of
-# interaction lengths near the DEL threshold (pumas.c:5644), both in the mixed
-# energy loss mode.
-MAX_OFF = 4e-3
-# Largest relative difference tolerated on a track that stayed in sync. Above
-# the last grid node (1e9 GeV) the mixed mode inverts the number of interaction
-# lengths through exp(b (nI - nI0) / cs) (pumas.c:3971-3981), a difference of
-# two large numbers: a 1 ulp difference between the two libm is amplified to
-# ~1e-3 on a few tracks per 10^4.
-MAX_REL = {"above_grid_mixed": 1e-2}
+# Bounds per workload: (largest fraction of tracks whose event sequence
+# diverges, largest fraction of in-sync tracks above RTOL, largest relative
+# difference of an in-sync track). Default: nothing diverges, nothing above
+# 1e-9. The exceptions are the values measured on B200 (profiles/parity_r2.json,
+# written by profiles/tools/parity_report.py with these numbers of tracks)
+# times a margin of ~5 for the statistics of a handful of tracks:
+#  - the long tracks of the stepping kernels (1350 .. 1770 Monte Carlo steps,
+#    each with <= 2 ulp differences between the host and device libm): 1 track
+#    in 1e5 at 3e-9 (headline), 3 in 2e4 at 4e-9 (rock_3km);
+#  - one track of limits_all / vertex_stop that ends 1e-8 / 1e-9 away;
+#  - the mixed energy loss mode, ill-conditioned in the reference itself: the
+#    single precision DCS interpolation (pumas.c:11279-11346, one float ulp =
+#    6e-8), the inversion of the number of interaction lengths near the DEL
+#    threshold (pumas.c:5644) and, above the last grid node, exp(b (nI - nI0) /
+#    cs) (pumas.c:3971-3981), which amplifies one ulp to 2e-3;
+#  - tau_ice: 4 tracks in 1e5 take another branch at a decay vertex.
+DEFAULT_BOUNDS = (0., 0., 1e-9)
+BOUNDS = {
+    "headline": (0., 1e-4, 3e-8),
+    "rock_3km": (0., 1e-3, 4e-8),
+    "limits_all": (0., 2e-4, 1e-7),
+    "vertex_stop": (0., 1e-4, 1e-8),
+    "tau_ice": (3e-4, 0., 1e-9),
+    "mixed_loss": (0., 1e-3, 3e-4),
+    "mixed_loss_scattering": (0., 1e-2, 1e-5),
+    "geometry_fast": (0., 1e-3, 3e-5),
+    "above_grid_mixed": (0., 1e-3, 3e-2),
+}
 
 _cache = {}
 
@@ -86,17 +104,21 @@ def test_parity(name):
     assert rc == 0
     sg, eg, mg, rg, steps = run_gpu(physics, w, seed=7, offset=1000)
     c = harness.compare_states(so, sg, eo, eg, ro, rg, rtol=RTOL)
-    frac = c["n_diverged"] / c["n"]
-    print("\n%s: n=%d match=%d bitexact=%d diverged=%d (%.2e) max_rel=%.3g "
-          "steps/track=%.1f" % (name, c["n"], c["n_match"], c["n_bitexact"],
-                                c["n_diverged"], frac, c["max_rel"],
-                                steps.mean()))
-    n_off = c["n"] - c["n_match"]
-    assert n_off / c["n"] <= MAX_OFF, (n_off, c["n_diverged"], c["max_rel"])
-    # in-sync tracks off the tolerance stay far below any physical relevance
-    assert c["max_rel"] < MAX_REL.get(name, 1e-4)
     sync = ~c["diverged"]
+    n_off = int(((c["worst"] > RTOL) & sync).sum())
+    print("\n%s: n=%d match=%d bitexact=%d diverged=%d off_in_sync=%d "
+          "max_rel=%.3g steps/track=%.1f" % (
+              name, c["n"], c["n_match"], c["n_bitexact"], c["n_diverged"],
+              n_off, c["max_rel"], steps.mean()))
+    max_div, max_off, max_rel = BOUNDS.get(name, DEFAULT_BOUNDS)
+    assert c["n_diverged"] <= max_div * n, (c["n_diverged"], n)
+    assert n_off <= max_off * n, (n_off, n, c["max_rel"])
+    assert c["max_rel"] <= max_rel, c["max_rel"]
     assert (mo[sync] == mg[sync]).all()
+    # the diverged tracks are still samples of the same distribution
+    if c["n_diverged"] > 0:
+        assert abs(so["energy"].mean() - sg["energy"].mean()) <= \
+            5. * so["energy"].std() / np.sqrt(n) + 1e-12
 
 
 def test_device_pointers_and_offsets():
