@@ -5,11 +5,14 @@
 
 Workload ("headline"): forward transport of 1 TeV muons
 through 1 km of standard rock, straggled energy loss + mixed scattering,
-distance limit. A "step" is one pass of pumas_context_transport_n over one
-batch of --tracks synthetic tracks per GPU. Tracks shard across ranks by
-contiguous track id ranges (weak scaling: per GPU work is fixed); the only
-exchange is one NCCL all-reduce per step of the tally vector (sum w, sum w^2,
-counts per energy bin), as in BASELINE.json's north_star.
+distance limit. A "step" is one pass of the batched transport entry point over
+one batch of --tracks synthetic tracks per GPU. Tracks shard across ranks by
+contiguous track id ranges (weak scaling: per GPU work is fixed); the tallies
+(sum w, sum w^2, counts per energy bin) are accumulated on the device across
+the steps and all-reduced ONCE at the end of the timed region, by the library
+itself (pumas_b200_comm_allreduce, NCCL), as in BASELINE.json's north_star.
+Nothing is waited for between the steps of the timed region
+(pumas_b200_context_transport_async; one pumas_b200_context_synchronize).
 
 One JSON line is printed by rank 0:
   value     whole-job tracks/s, inputs resident in HBM when the timed region
@@ -59,6 +62,8 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=0,
                     help="tracks of the CPU baseline sample (0: auto)")
     ap.add_argument("--workload", default="headline")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip the other BASELINE configurations")
     return ap.parse_args()
 
 
@@ -117,6 +122,20 @@ def reference_rate(workload, n, threads):
     return n / out[5], float(out[3].mean())
 
 
+def shared_config(n):
+    """The `config` object, identical for the two arms (the reference arm times
+    a bounded sample of the same workload: its size is under `details`)."""
+    return {
+        "workload": WORKLOAD,
+        "rng": "Philox4x32-10 keyed by (seed, track id)",
+        "sharding": "contiguous track id ranges per rank, no data-path "
+                    "collective; tallies accumulated on the device and "
+                    "all-reduced ONCE at the end of the run (NCCL, in-library)",
+        "l2": "inputs larger than L2: %d MB of states per step and per GPU "
+              "against 126 MB" % (n * 104 >> 20),
+    }
+
+
 def run_reference(args):
     """--impl reference: the CPU reference alone, same schema."""
     rank = int(os.environ.get("RANK", "0"))
@@ -144,9 +163,11 @@ def run_reference(args):
         "ms_per_step": 1e3 * elapsed / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": WORKLOAD, "tracks_per_step": n,
-                   "note": "CPU reference: unmodified src/pumas.c, one "
-                           "pumas_context per thread, Philox callback"},
+        "config": shared_config(args.tracks),
+        "details": {"tracks_per_step": n,
+                    "note": "CPU reference: unmodified src/pumas.c, one "
+                            "pumas_context per thread, Philox callback; each "
+                            "step is a bounded sample of the workload"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads,
                          "kind": "reference",
                          "sample": "%d tracks per step" % n},
@@ -155,6 +176,88 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+# The other BASELINE.json configurations, measured after the timed region of
+# the headline (one warm-up + three launches each, states resident in HBM; the
+# MEDIAN launch counts: a backward batch now and then holds one track that runs
+# away above the energy grid, where the rejection loop of the reference's hard
+# elastic sampling (pumas.c:5843-5868) draws millions of variates, and the
+# whole launch waits for it -- 1 track in 2e6 of `straight_mixed`):
+# (workload of tests/workloads.py, tracks per launch, bound, algorithmic flop
+# per Monte Carlo step or bytes per track).
+EXTRA = [
+    ("straight", 1 << 22, "fp64", 350.),          # configs[0], no scattering
+    ("straight_mixed", 1 << 21, "fp64", 600.),    # configs[0], mixed
+    ("csda_water", 1 << 23, "hbm", 212.),         # configs[1]
+    ("rock_3km", 1 << 20, "fp64", 600.),          # configs[2]
+    ("geometry_detailed", 1 << 19, "fp64", 600.),  # configs[3], one direction
+    ("tau_ice", 1 << 21, "fp64", 600.),           # configs[4]
+]
+
+
+def measured_hbm_peak():
+    """GB/s of MEASURED_PEAKS.json (driver written), else the fallback of
+    B200_PROFILING.md."""
+    try:
+        return float(json.load(open(os.path.join(
+            ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650., "fallback"
+
+
+def run_extra(pb, harness, WORKLOADS, torch, np, peak_tflops):
+    out = {}
+    hbm, hbm_kind = measured_hbm_peak()
+    stream = torch.cuda.current_stream()
+    cache = {}
+    for name, n, bound, unit_cost in EXTRA:
+        try:
+            dump, builder, kwargs = WORKLOADS[name]
+            if dump not in cache:
+                cache[dump] = pb.Physics(harness.dump_path(dump))
+            physics = cache[dump]
+            w = builder(physics.material_index, n, **kwargs)
+            ctx = pb.Context(physics, seed=2026)
+            ctx.configure(w["settings"])
+            ctx.geometry(w["geometry"])
+            ctx.stream(stream.cuda_stream)
+            pristine = torch.from_numpy(
+                w["states"].view(np.uint8).reshape(n, 104).copy()).cuda()
+            work = torch.empty_like(pristine)
+            events = torch.zeros(n, dtype=torch.int32, device="cuda")
+            ms = []
+            for k in range(4):
+                work.copy_(pristine, non_blocking=True)
+                ctx.track_offset(k * n)
+                e0 = torch.cuda.Event(enable_timing=True)
+                e1 = torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ctx.transport_async(n, work.data_ptr(), events.data_ptr())
+                e1.record()
+                ctx.synchronize()
+                if k > 0:
+                    ms.append(e0.elapsed_time(e1))
+            _, nsteps = ctx.last_counters(n)
+            steps = float(nsteps.mean())
+            t = sorted(ms)[len(ms) // 2] * 1e-3
+            row = {"tracks_per_s": n / t, "tracks_per_launch": n,
+                   "launch_ms": [round(x, 3) for x in ms],
+                   "steps_per_track": steps, "bound": bound}
+            if bound == "hbm":
+                row["achieved_GBps"] = unit_cost * n / t * 1e-9
+                row["peak_GBps"] = hbm
+                row["peak_kind"] = hbm_kind
+                row["roofline_frac"] = row["achieved_GBps"] / hbm
+            else:
+                row["achieved_TFLOPs"] = unit_cost * steps * n / t * 1e-12
+                row["roofline_frac"] = (row["achieved_TFLOPs"] / peak_tflops
+                                        if peak_tflops else None)
+            out[name] = row
+            del ctx, pristine, work, events
+        except Exception as exc:  # an extra must not lose the headline line
+            out[name] = {"error": "%s: %s" % (type(exc).__name__, exc)}
+    return out
 
 
 def main():
@@ -177,10 +280,18 @@ def main():
         raise SystemExit("bench.py needs a B200: no usable CUDA device "
                          "(there is no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    comm = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device(
             "cuda", local_rank))
+
+        def exchange(uid):
+            box = [uid]
+            dist.broadcast_object_list(box, src=0)
+            return box[0]
+        # the library's own communicator: the one collective of the data path
+        comm = pb.Comm(rank, world, exchange)
 
     def barrier():
         if world > 1:
@@ -204,46 +315,65 @@ def main():
     pristine = host.cuda()
     work = torch.empty_like(pristine)
     events = torch.zeros(n, dtype=torch.int32, device="cuda")
-    tally = torch.zeros(4 + TALLY_BINS, dtype=torch.float64, device="cuda")
+    n_tally = 4 + TALLY_BINS
+    tally = torch.zeros(n_tally, dtype=torch.float64, device="cuda")
+    total = torch.zeros(n_tally, dtype=torch.float64, device="cuda")
     scratch = torch.zeros(pb.tally_scratch_bytes(TALLY_BINS), dtype=torch.uint8,
                           device="cuda")
-    from pumas_b200.sharding import allreduce_tallies, step_offset
+    from pumas_b200.sharding import step_offset
 
-    def step(k):
-        """One pass of the hot path over this rank's batch, HBM resident."""
-        work.copy_(pristine, non_blocking=True)
-        ctx.track_offset(step_offset(k, rank, world, n))
-        ctx.transport_device(n, work.data_ptr(), events.data_ptr())
-        pb.tally(work.data_ptr(), events.data_ptr(), n,
-                 pb.EVENT_LIMIT_DISTANCE, 1e-3, 1e3, TALLY_BINS,
-                 tally.data_ptr(), scratch.data_ptr(), stream.cuda_stream)
-        allreduce_tallies(tally)
-        return ctx.last_kernel_time()
+    def run(first, count, stamps=None):
+        """`count` passes of the hot path over this rank's batch, states
+        resident in HBM, nothing waited for: every pass enqueues the restore
+        of the inputs, the transport, the tally of the batch and its
+        accumulation; then ONE all-reduce of the accumulated tallies."""
+        total.zero_()
+        for k in range(count):
+            work.copy_(pristine, non_blocking=True)
+            ctx.track_offset(step_offset(first + k, rank, world, n))
+            if stamps is not None:
+                stamps[k][0].record()
+            ctx.transport_async(n, work.data_ptr(), events.data_ptr())
+            if stamps is not None:
+                stamps[k][1].record()
+            pb.tally(work.data_ptr(), events.data_ptr(), n,
+                     pb.EVENT_LIMIT_DISTANCE, 1e-3, 1e3, TALLY_BINS,
+                     tally.data_ptr(), scratch.data_ptr(), stream.cuda_stream)
+            pb.tally_accumulate(total.data_ptr(), tally.data_ptr(), n_tally,
+                                stream.cuda_stream)
+        if comm is not None:
+            comm.allreduce(total.data_ptr(), n_tally, stream.cuda_stream)
+        ctx.synchronize()
 
-    for k in range(args.warmup):
-        step(k)
+    run(0, args.warmup)
     barrier()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches, steps_total = 0., 0, 0
+    stamps = [(torch.cuda.Event(enable_timing=True),
+               torch.cuda.Event(enable_timing=True))
+              for _ in range(args.steps)]
     barrier()
     e0.record()
-    for k in range(args.steps):
-        ms, nl = step(args.warmup + k)
-        kernel_ms += ms
-        launches += nl + 2  # transport kernel + the two tally kernels
+    run(args.warmup, args.steps, stamps)
     e1.record()
     barrier()
-    sampler.stop_flag.set()
+    if sampler is not None:
+        sampler.stop_flag.set()
     elapsed_ms = e0.elapsed_time(e1)
+    kernel_ms = sum(a.elapsed_time(b) for a, b in stamps)
+    _, launches_per_step = ctx.last_kernel_time()
+    # transport kernels + the two tally kernels + the accumulation
+    launches = args.steps * (launches_per_step + 3)
     nrand, nsteps = ctx.last_counters(n)
     steps_per_track = float(nsteps.mean())
-    survival = float(tally[3].item() / tally[2].item()) if tally[2].item() else 0.
+    totals = total.cpu().numpy()
+    survival = float(totals[3] / totals[2]) if totals[2] else 0.
 
-    # End to end: host (pinned) buffers through the same C-ABI call.
+    # End to end: host (pinned) buffers through the reference-facing call.
     host_np = host.numpy().reshape(-1).view(pb.STATE_DTYPE)
     e2e_buf = torch.empty_like(host).pin_memory()
     e2e_np = e2e_buf.numpy().reshape(-1).view(pb.STATE_DTYPE)
@@ -277,39 +407,34 @@ def main():
         flop_per_launch = FLOP_PER_STEP * steps_per_track * n
         achieved = flop_per_launch / (kernel_ms / args.steps * 1e-3) * 1e-12
         cpu = None
-        if (world == 1) and harness.have_oracle():
-            threads = os.cpu_count() or 1
-            sample = args.cpu_sample or max(2000, 1500 * threads)
-            rate, _ = reference_rate(args.workload, sample, threads)
-            cpu = {"value": rate, "unit": UNIT, "cores": threads,
-                   "kind": "reference",
-                   "sample": "%d tracks of the same workload, reference "
-                             "src/pumas.c, one context per thread" % sample}
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            try:
-                t = json.load(open(tpath))
-                traffic = t["dram_bytes_per_track"] * n
-            except Exception:
-                traffic = None
+        extra = None
+        if world == 1:
+            if harness.have_oracle():
+                threads = os.cpu_count() or 1
+                sample = args.cpu_sample or max(2000, 1500 * threads)
+                rate, _ = reference_rate(args.workload, sample, threads)
+                cpu = {"value": rate, "unit": UNIT, "cores": threads,
+                       "kind": "reference",
+                       "sample": "%d tracks of the same workload, reference "
+                                 "src/pumas.c, one context per thread" % sample}
+            if not args.no_extra:
+                extra = run_extra(pb, harness, WORKLOADS, torch, np, peak)
+        config = shared_config(n)
+        if extra is not None:
+            config["extra"] = extra
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {
-                "workload": WORKLOAD, "tracks_per_step_per_gpu": n,
+            "config": config,
+            "details": {
+                "tracks_per_step_per_gpu": n,
                 "steps_per_track": steps_per_track,
                 "survival_fraction": survival,
-                "l2": "inputs %d MB per step and per GPU (%s the 126 MB L2)" % (
-                    n * 104 >> 20,
-                    "larger than" if n * 104 > 126 << 20 else "NOT larger than"),
-                "sharding": "contiguous track id ranges per rank, one NCCL "
-                            "all-reduce of %d tally doubles per step" % (
-                                4 + TALLY_BINS),
-                "rng": "Philox4x32-10 keyed by (seed, track id)"},
+                "tallies": "%d doubles per rank, %d collective(s) in the "
+                           "timed region" % (n_tally, 1 if world > 1 else 0)},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": n * 104,
@@ -318,16 +443,22 @@ def main():
             "roofline": {
                 "bound": "fp64", "achieved": achieved, "peak": peak,
                 "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": traffic,
+                "traffic": None,
                 "note": "algorithmic flop = %.0f flop/step x %.1f steps/track "
-                        "x %d tracks per launch; peak = DFMA peak measured "
-                        "live (pumas_b200_fp64_peak); HBM is not the bound: "
-                        "%.0f B/track algorithmic" % (
+                        "x %d tracks per launch over the CUDA-event duration "
+                        "of the transport kernel; peak = DFMA peak measured "
+                        "live (pumas_b200_fp64_peak; MEASURED_PEAKS.json has "
+                        "no FP64 entry); HBM is not the bound (%.0f B/track "
+                        "algorithmic); traffic: not measurable from inside "
+                        "the run, see the ncu capture profiles/r2_hot_ncu.txt "
+                        "(dram bytes per launch)" % (
                             FLOP_PER_STEP, steps_per_track, n, 212.)},
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
         print(json.dumps(line))
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
 

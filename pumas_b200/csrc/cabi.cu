@@ -139,6 +139,14 @@ enum pumas_return raise(pumas_function_t * caller, enum pumas_return rc,
 /* ---- device helpers -------------------------------------------------------- */
 int device_usable(std::string * why)
 {
+        /* (cudaGetDeviceProperties costs milliseconds: asked once per device) */
+        static int usable[64] = { 0 };
+        {
+                int dev = -1;
+                if ((cudaGetDevice(&dev) == cudaSuccess) && (dev >= 0) &&
+                    (dev < 64) && usable[dev])
+                        return 1;
+        }
         int count = 0;
         const cudaError_t e = cudaGetDeviceCount(&count);
         if ((e != cudaSuccess) || (count <= 0)) {
@@ -163,6 +171,7 @@ int device_usable(std::string * why)
                             "carries sm_100a code only";
                 return 0;
         }
+        if ((dev >= 0) && (dev < 64)) usable[dev] = 1;
         return 1;
 }
 

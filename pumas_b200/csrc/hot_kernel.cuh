@@ -838,19 +838,25 @@ cudaError_t launch_hot(const Physics & p, const Physics & host_view,
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (sms > 160) sms = 160; /* (the mirrors of the workspace) */
         if ((t.grid_cap > 1) && (t.grid_cap < sms)) sms = t.grid_cap;
-        /* stepping CTAs for the batch, service CTAs for them: one in 9 (B200,
-         * headline workload, of 148: 10 -> 1.52e6, 12 -> 1.78e6, 14 -> 2.06e6,
-         * 16 -> 2.30e6, 18 -> 2.29e6, 21 -> 2.23e6 tracks/s;
-         * profiles/r2_experiments.md) */
+        /* stepping CTAs for the batch, service CTAs for them. Measured on B200
+         * (148 SMs; profiles/r2_experiments.md), tracks/s against the number
+         * of service CTAs: headline 14 -> 2.06e6, 16 -> 2.30e6, 18 -> 2.29e6,
+         * 21 -> 2.23e6; rock_3km 16 -> 1.36e6, 21 -> 1.41e6; backward
+         * (straight.c, three times as many hard inelastic events per step)
+         * 16 -> 8.3e6, 21 -> 9.4e6, 28 -> 8.8e6 without scattering and
+         * 16 -> 5.6e6, 21 -> 6.7e6, 28 -> 6.8e6 with. Below the optimum the
+         * stepping CTAs starve: one SM in 8 forward, one in 6 backward. */
         const long per_cta = (long)HOT_CTA_SLOTS;
         const long want = (n + per_cta - 1) / per_cta;
-        int n_service = (t.del_ctas > 0) ? t.del_ctas : (sms + 4) / 9;
+        int n_service = (t.del_ctas > 0) ?
+            t.del_ctas :
+            ((Cfg::direction == MODE_FORWARD) ? sms / 8 : sms / 6);
         if (n_service > sms - 1) n_service = sms - 1;
         if (n_service < 1) return cudaErrorInvalidConfiguration;
         int n_step = (want < (long)(sms - n_service)) ? (int)want :
                                                         sms - n_service;
         if (t.del_ctas <= 0) {
-                const int need = (n_step + 7) / 8;
+                const int need = (n_step + 5) / 6;
                 if (need < n_service) n_service = need;
         }
         hot_workspace_init<<<(HOT_QUEUE + 255) / 256, 256, 0, stream>>>(
