@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "pb_dump.hpp"
+#include "pb_csda.h"
 #include "pb_hot.h"
 #include "pb_transport.h"
 #include "philox.h"
@@ -144,6 +145,49 @@ void run_tracks_hot(Job * job, const Cfg & cfg, const pb::UniformGeometry & geo)
         }
 }
 
+/* The lean closed form CSDA of the GPU kernel (pb_csda.h), with the general
+ * transport_track behind it. */
+template <class Cfg>
+void run_tracks_csda(Job * job, const Cfg & cfg, const pb::UniformGeometry & geo)
+{
+        using namespace pb;
+        const Physics & p = job->hp->view;
+        const CsdaCtx c = csda_context(p, p, cfg, geo.material);
+        for (long i = job->begin; i < job->end; i++) {
+                PhiloxRng rng;
+                pb_philox_init(&rng.g, job->seed, job->offset + (uint64_t)i);
+                unsigned int steps = 0;
+                Outcome out;
+                if (!csda_track(cfg, c, job->states[i], out))
+                        out = transport_track(
+                            p, cfg, geo, rng, job->states[i], &steps);
+                if ((out.rc != 0) && (job->rc == 0)) job->rc = out.rc;
+                if (job->events) job->events[i] = out.event;
+                if (job->media) {
+                        job->media[2 * i] = out.medium[0];
+                        job->media[2 * i + 1] = out.medium[1];
+                }
+                if (job->n_random) job->n_random[i] = rng.g.count;
+                if (job->n_steps) job->n_steps[i] = steps;
+        }
+}
+
+template <int DI> bool try_csda(Job * job)
+{
+        typedef pb::StaticSettings<pb::MODE_CSDA, pb::MODE_DISABLED, DI,
+            pb::MODE_WEIGHTED>
+            Cfg;
+        const pumas_b200_geometry & geo = *job->geo;
+        if (!Cfg::matches(job->cfg) ||
+            (geo.kind != PUMAS_B200_GEOMETRY_UNIFORM) || geo.layer[0].has_locals)
+                return false;
+        pb::UniformGeometry ug;
+        ug.material = geo.layer[0].material;
+        ug.step_type = geo.step_type;
+        run_tracks_csda(job, Cfg(job->cfg), ug);
+        return true;
+}
+
 template <int EL, int SC, int DI, int DE> bool try_specialised(Job * job)
 {
         typedef pb::StaticSettings<EL, SC, DI, DE> Cfg;
@@ -165,6 +209,9 @@ void * worker(void * arg)
 {
         Job * job = static_cast<Job *>(arg);
         using namespace pb;
+        if ((g_specialise == 2) &&
+            (try_csda<MODE_FORWARD>(job) || try_csda<MODE_BACKWARD>(job)))
+                return NULL;
         if (g_specialise &&
             (try_specialised<MODE_STRAGGLED, MODE_MIXED, MODE_FORWARD,
                  MODE_WEIGHTED>(job) ||

@@ -26,6 +26,7 @@ N_TRACKS = {
     "headline": 100000, "rock_3km": 20000, "straight": 100000,
     "straight_mixed": 50000, "csda_water": 200000,
     "csda_spectrum_fwd": 100000, "csda_spectrum_bwd": 100000,
+    "csda_limits_fwd": 100000, "csda_limits_bwd": 100000,
     "mixed_loss": 100000, "mixed_loss_scattering": 20000,
     "mixed_loss_bwd": 40000, "csda_magnet_fwd": 100000,
     "csda_magnet_bwd": 100000, "models_kkb_fwd": 20000,

@@ -50,7 +50,11 @@ PB_SPECIALISATION(launch_spec_straggled_mixed_forward);
 PB_SPECIALISATION(launch_spec_straggled_mixed_backward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_forward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_backward);
-PB_SPECIALISATION(launch_spec_csda);
+bool launch_spec_csda(const Physics & p, const Physics & host_view,
+    const Settings & cfg, const Geometry & geo, uint64_t seed, uint64_t offset,
+    long n, State * states, int * events, int * media, int * status,
+    unsigned int * n_random, unsigned int * n_steps, void * workspace,
+    int kernel, cudaStream_t stream, cudaError_t * error);
 
 /* hot_kernel.cuh instantiations (kernels_hot*.cu) */
 #define PB_HOT_SPECIALISATION(NAME)                                            \
@@ -103,11 +107,14 @@ cudaError_t launch_transport(const Physics & p, const Physics & host_view,
         }
         if ((kernel == KERNEL_RESIDENT) || (kernel == KERNEL_RESIDENT_SPEC)) {
                 cudaError_t e = cudaSuccess;
+                if (launch_spec_csda(p, host_view, cfg, geo, seed, offset, n,
+                        states, events, media, status, n_random, n_steps,
+                        workspace, kernel, stream, &e))
+                        return e;
 #define TRY(NAME)                                                              \
         if (NAME(p, cfg, geo, seed, offset, n, states, events, media, status,  \
                 n_random, n_steps, workspace, stream, &e))                     \
                 return e;
-                TRY(launch_spec_csda)
                 TRY(launch_spec_straggled_mixed_forward)
                 TRY(launch_spec_straggled_mixed_backward)
                 TRY(launch_spec_straggled_noscat_forward)

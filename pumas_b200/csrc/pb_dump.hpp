@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "pb_atomic_data.h"
+#include "pb_csda_tables.h"
 #include "pb_hot_tables.h"
 #include "pb_physics.h"
 
@@ -429,8 +430,37 @@ inline int load_physics_bytes(
             (detail::align16(o_elt + nel * sizeof(Element)) + 255) &
             ~(size_t)255;
         const size_t o_hotX = o_hotK + nm * n_cells * HOTK_WORDS * sizeof(double);
-        const size_t total = detail::align16(
+        const size_t o_csdaK = detail::align16(
             o_hotX + nm * n_cells * HOTX_WORDS * sizeof(double));
+        const size_t o_csdaX =
+            o_csdaK + nm * n_cells * CSDAK_WORDS * sizeof(double);
+        const size_t o_loc = detail::align16(
+            o_csdaX + nm * n_cells * CSDAX_WORDS * sizeof(double));
+        /* (the key ranges of the locators: from the tables in the blob) */
+        int locK_min = 0, locK_keys = 1, locX_min = 0, locX_keys = 1;
+        if (ok && (ne > 1)) {
+                const double * K = reinterpret_cast<const double *>(
+                    blob + off(h.table_K, ne * sizeof(double)));
+                const double * X = reinterpret_cast<const double *>(blob +
+                    off(h.table_X, N_SCHEMES * nm * ne * sizeof(double)));
+                if (ok) {
+                        locator_range(K, (int)ne, &locK_min, &locK_keys);
+                        int lo = 0, hi = 0;
+                        for (size_t m = 0; m < nm; m++) {
+                                int kmin, nk;
+                                locator_range(X + m * ne, (int)ne, &kmin, &nk);
+                                if ((m == 0) || (kmin < lo)) lo = kmin;
+                                if ((m == 0) || (kmin + nk > hi)) hi = kmin + nk;
+                        }
+                        locX_min = lo;
+                        locX_keys = hi - lo;
+                }
+        }
+        const size_t o_locK = o_loc;
+        const size_t o_locX =
+            detail::align16(o_locK + (size_t)locK_keys * sizeof(unsigned short));
+        const size_t total = detail::align16(
+            o_locX + nm * (size_t)locX_keys * sizeof(unsigned short));
         hp.image.assign(total, 0);
         std::memcpy(hp.image.data() + o_blob, blob, size);
         std::memcpy(hp.image.data() + o_coff, comp_offset.data(), (nm + 1) * 4);
@@ -526,6 +556,14 @@ inline int load_physics_bytes(
         PB_RELOC(element, o_elt);
         PB_RELOC(hotK, o_hotK);
         PB_RELOC(hotX, o_hotX);
+        PB_RELOC(csdaK, o_csdaK);
+        PB_RELOC(csdaX, o_csdaX);
+        PB_RELOC(locK, o_locK);
+        PB_RELOC(locX, o_locX);
+        v.locK_min = locK_min;
+        v.locK_keys = locK_keys;
+        v.locX_min = locX_min;
+        v.locX_keys = locX_keys;
 #undef PB_RELOC
         if (!ok) {
                 err = "corrupted binary dump (pointer outside of the blob)";
@@ -535,6 +573,17 @@ inline int load_physics_bytes(
         hot_tables_build(hp.view,
             reinterpret_cast<double *>(hp.image.data() + o_hotK),
             reinterpret_cast<double *>(hp.image.data() + o_hotX));
+        csda_tables_build(hp.view,
+            reinterpret_cast<double *>(hp.image.data() + o_csdaK),
+            reinterpret_cast<double *>(hp.image.data() + o_csdaX));
+        locator_build(hp.view.K, (int)ne, locK_min, locK_keys,
+            reinterpret_cast<unsigned short *>(hp.image.data() + o_locK));
+        for (size_t m = 0; m < nm; m++)
+                locator_build(col_sm(hp.view, hp.view.X, MODE_CSDA, (int)m),
+                    (int)ne, locX_min, locX_keys,
+                    reinterpret_cast<unsigned short *>(
+                        hp.image.data() + o_locX) +
+                        m * (size_t)locX_keys);
         return 0;
 }
 

@@ -115,6 +115,14 @@ struct Physics {
          * [material][cell][HOTX_WORDS]. */
         const double * hotK;
         const double * hotX;
+        /* The same for the closed form CSDA (pb_csda.h): packed records of
+         * the CSDA scheme and the O(1) locators of the kinetic grid and of the
+         * grammage column of every material (a common key range). */
+        const double * csdaK;
+        const double * csdaX;
+        const unsigned short * locK;
+        const unsigned short * locX; /* [material][locX_keys] */
+        int locK_min, locK_keys, locX_min, locX_keys;
 };
 
 /* ---- table accessors, pumas.c:4260-4752 -------------------------------- */

@@ -92,13 +92,15 @@ def csda_magnet(material, n, seed=0, direction=MODE_FORWARD):
                            direction=isotropic(n, seed + 2)))
 
 
-def csda_spectrum(material, n, seed=0, direction=MODE_FORWARD):
-    """Closed form CSDA over 10 decades of energy with every limit armed."""
+def csda_spectrum(material, n, seed=0, direction=MODE_FORWARD, time=True):
+    """Closed form CSDA over 10 decades of energy with every limit armed
+    (`time=False`: all but the proper time limit, which the lean CSDA kernel
+    hands to the general code)."""
     return dict(
         settings=make_settings(
             MODE_CSDA, MODE_DISABLED, direction=direction,
             event=(EVENT_LIMIT_DISTANCE | EVENT_LIMIT_GRAMMAGE |
-                   EVENT_LIMIT_ENERGY | EVENT_LIMIT_TIME),
+                   EVENT_LIMIT_ENERGY | (EVENT_LIMIT_TIME if time else 0)),
             limit_distance=300., limit_grammage=5e5,
             limit_energy=(1e-2 if direction == MODE_FORWARD else 1e5),
             limit_time=250.),
@@ -277,6 +279,9 @@ WORKLOADS = {
     "csda_spectrum_fwd": ("materials.muon", csda_spectrum, {}),
     "csda_spectrum_bwd": ("materials.muon", csda_spectrum,
                           dict(direction=MODE_BACKWARD)),
+    "csda_limits_fwd": ("materials.muon", csda_spectrum, dict(time=False)),
+    "csda_limits_bwd": ("materials.muon", csda_spectrum,
+                        dict(direction=MODE_BACKWARD, time=False)),
     "csda_magnet_fwd": ("materials.muon", csda_magnet, {}),
     "csda_magnet_bwd": ("materials.muon", csda_magnet,
                         dict(direction=MODE_BACKWARD)),
