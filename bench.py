@@ -260,10 +260,35 @@ def run_extra(pb, harness, WORKLOADS, torch, np, peak_tflops):
     return out
 
 
+class QuietStdout:
+    """stdout carries ONE JSON line: anything a library prints meanwhile (NCCL
+    writes its version banner to stdout) goes to stderr instead."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
 def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    with QuietStdout():
+        line = measure(args)
+    if line is not None:
+        print(json.dumps(line))
+
+
+def measure(args):
+    """Returns the JSON object on rank 0, None elsewhere."""
 
     import numpy as np
     import torch
@@ -456,11 +481,13 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+    else:
+        line = None
     if comm is not None:
         comm.close()
     if world > 1:
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":

@@ -350,6 +350,14 @@ void port_philox_uniforms(uint64_t seed, uint64_t track, int n, double * out)
         for (int i = 0; i < n; i++) out[i] = pb_philox_uniform(&g);
 }
 
+/* The device logarithm of a uniform variate (tests/test_hot_math.py). */
+double port_hot_log_uniform(uint32_t w) { return pb::hot_log_uniform(w); }
+
+void port_hot_log_uniform_n(const uint32_t * w, long n, double * out)
+{
+        for (long i = 0; i < n; i++) out[i] = pb::hot_log_uniform(w[i]);
+}
+
 /* Single precision libm restatements (tests/test_libm_float.py). */
 float port_logf(float x) { return pb::logf_libm(x); }
 float port_expf(float x) { return pb::expf_libm(x); }

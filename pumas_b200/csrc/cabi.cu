@@ -1227,8 +1227,20 @@ enum pumas_return transport_batch(pumas_function_t * caller,
         if (physics == nullptr)
                 return RAISE_C(PUMAS_RETURN_PHYSICS_ERROR,
                     "the Physics has not been initialised");
-        if (!c->has_geometry)
+        if (!c->has_geometry) {
+                /* a host `pumas_medium_cb` cannot run inside a kernel: say so
+                 * instead of ignoring it */
+                if (context->medium != nullptr)
+                        return RAISE_C(PUMAS_RETURN_MEDIUM_ERROR,
+                            "context->medium is a host callback: it cannot "
+                            "run on the device. Describe the geometry with "
+                            "pumas_b200_context_geometry_set");
                 return RAISE_C(PUMAS_RETURN_MEDIUM_ERROR, "no medium specified");
+        }
+        if (context->recorder != nullptr)
+                return RAISE_C(PUMAS_RETURN_VALUE_ERROR,
+                    "context->recorder is a host object: the device kernels "
+                    "do not record frames (not implemented)");
 
         /* Configuration checks, pumas.c:3152-3177. */
         const pb::Settings cfg = settings_from(context);

@@ -10,6 +10,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 
 #include "kernels.h"
 #include "pb_transport.h"
@@ -139,7 +140,8 @@ struct Tunables {
 inline const Tunables & tunables()
 {
         static Tunables t = { 0, 0, 0, 0, 0, nullptr, 0 };
-        if (t.sms != 0) return t;
+        static std::once_flag once;
+        std::call_once(once, []() {
         const char * v;
         if ((v = getenv("PUMAS_B200_EHS_PERIOD")) != nullptr)
                 t.ehs_period = atoi(v);
@@ -155,6 +157,7 @@ inline const Tunables & tunables()
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&t.sms, cudaDevAttrMultiProcessorCount, dev);
+        });
         return t;
 }
 
@@ -179,7 +182,8 @@ inline int device_sms(int dev)
  * pumas_b200_context_last_kernel_time). */
 inline int & last_launch_count()
 {
-        static int n = 0;
+        /* (per host thread: one context per thread, as the reference) */
+        static thread_local int n = 0;
         return n;
 }
 

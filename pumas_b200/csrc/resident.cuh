@@ -456,7 +456,10 @@ __device__ __forceinline__ void park_exchange(Resident & s, RingRng & rng,
 #undef PARK_W
 #undef PARK_ST
 
-/* A ring of entry indices in shared memory, many producers, many consumers. */
+/* A ring of entry indices in shared memory, many producers, many consumers.
+ * The slot arrays hold 2 x ENTRIES slots for at most ENTRIES indices in
+ * flight: a producer that wraps around cannot reach a slot whose consumer has
+ * claimed it (head advanced) but not read it yet. */
 struct Ring {
         unsigned int head, tail;
 };
@@ -466,7 +469,7 @@ __device__ __forceinline__ void ring_push(
     volatile unsigned short * slots, Ring * r, int e)
 {
         const unsigned int pos = atomicAdd(&r->tail, 1u);
-        slots[pos & (ENTRIES - 1)] = (unsigned short)e;
+        slots[pos & (2 * ENTRIES - 1)] = (unsigned short)e;
 }
 
 __device__ __forceinline__ int ring_available(const Ring * r)
@@ -506,7 +509,8 @@ __device__ __forceinline__ int ring_pop_warp(volatile unsigned short * slots,
         const int rank = __popc(m & ((1u << lane) - 1u));
         int e = -1;
         if (want && (rank < n)) {
-                const unsigned int at = (h + (unsigned int)rank) & (ENTRIES - 1);
+                const unsigned int at =
+                    (h + (unsigned int)rank) & (2 * ENTRIES - 1);
                 do {
                         e = slots[at];
                 } while (e == RS_NONE);
@@ -631,7 +635,7 @@ struct OffloadHeader {
 };
 constexpr size_t RS_OFFLOAD_QUEUES = 256; /* byte offset of the queues */
 constexpr size_t RS_OFFLOAD_PARK =
-    RS_OFFLOAD_QUEUES + 3 * (size_t)RS_GENTRIES * sizeof(unsigned short);
+    RS_OFFLOAD_QUEUES + 6 * (size_t)RS_GENTRIES * sizeof(unsigned short);
 constexpr size_t RS_GPARK_BYTES =
     (size_t)RS_PARK_WORDS * RS_GENTRIES * sizeof(unsigned long long);
 static_assert(sizeof(OffloadHeader) <= RS_OFFLOAD_QUEUES, "header");
@@ -649,8 +653,8 @@ struct OffloadQueues {
                 h = reinterpret_cast<OffloadHeader *>(w);
                 free_q = reinterpret_cast<volatile unsigned short *>(
                     w + RS_OFFLOAD_QUEUES);
-                del_q = free_q + RS_GENTRIES;
-                ret_q = del_q + RS_GENTRIES;
+                del_q = free_q + 2 * RS_GENTRIES;
+                ret_q = del_q + 2 * RS_GENTRIES;
                 park = reinterpret_cast<unsigned long long *>(
                     w + RS_OFFLOAD_PARK);
         }
@@ -698,7 +702,8 @@ static __global__ void resident_offload_init(unsigned char * workspace)
         if (i < RS_GENTRIES) {
                 q[i] = (unsigned short)i;
                 q[RS_GENTRIES + i] = (unsigned short)RS_NONE;
-                q[2 * RS_GENTRIES + i] = (unsigned short)RS_NONE;
+                for (int k = 2; k < 6; k++)
+                        q[k * RS_GENTRIES + i] = (unsigned short)RS_NONE;
         }
 }
 
@@ -850,7 +855,7 @@ template <int WARPS>
 __host__ __device__ constexpr size_t resident_smem_bytes(bool pooled)
 {
         return ((sizeof(ResidentShared) + 15) & ~(size_t)15) +
-            3 * RS_ENTRIES * sizeof(unsigned short) +
+            6 * RS_ENTRIES * sizeof(unsigned short) +
             (size_t)RS_RING_WORDS * (32 * WARPS) * sizeof(uint32_t) +
             (size_t)WARPS * N_RSTATS * sizeof(unsigned long long) +
             RS_PARK_BYTES +
@@ -879,9 +884,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
             smem_raw + ((sizeof(ResidentShared) + 15) & ~(size_t)15);
         volatile unsigned short * const free_q =
             reinterpret_cast<volatile unsigned short *>(at);
-        volatile unsigned short * const del_q = free_q + RS_ENTRIES;
-        volatile unsigned short * const ret_q = del_q + RS_ENTRIES;
-        at += 3 * RS_ENTRIES * sizeof(unsigned short);
+        volatile unsigned short * const del_q = free_q + 2 * RS_ENTRIES;
+        volatile unsigned short * const ret_q = del_q + 2 * RS_ENTRIES;
+        at += 6 * RS_ENTRIES * sizeof(unsigned short);
         uint32_t * const rings = reinterpret_cast<uint32_t *>(at);
         at += (size_t)RS_RING_WORDS * RS_THREADS * sizeof(uint32_t);
         unsigned long long * const stats =
@@ -915,8 +920,9 @@ __global__ void __launch_bounds__(RS_THREADS, 1)
         }
         for (int e = threadIdx.x; e < RS_ENTRIES; e += RS_THREADS) {
                 free_q[e] = (unsigned short)e;
-                del_q[e] = (unsigned short)RS_NONE;
-                ret_q[e] = (unsigned short)RS_NONE;
+                free_q[RS_ENTRIES + e] = (unsigned short)RS_NONE;
+                del_q[e] = del_q[RS_ENTRIES + e] = (unsigned short)RS_NONE;
+                ret_q[e] = ret_q[RS_ENTRIES + e] = (unsigned short)RS_NONE;
         }
         __syncthreads();
 
