@@ -192,6 +192,7 @@ EXTRA = [
     ("csda_water", 1 << 23, "hbm", 212.),         # configs[1]
     ("rock_3km", 1 << 20, "fp64", 600.),          # configs[2]
     ("geometry_detailed", 1 << 19, "fp64", 600.),  # configs[3], one direction
+    ("geometry_grid", 48 * 8192, "fp64", 600.),   # configs[3], 6 x 8 grid
     ("tau_ice", 1 << 21, "fp64", 600.),           # configs[4]
 ]
 
@@ -253,6 +254,24 @@ def run_extra(pb, harness, WORKLOADS, torch, np, peak_tflops):
                 row["achieved_TFLOPs"] = unit_cost * steps * n / t * 1e-12
                 row["roofline_frac"] = (row["achieved_TFLOPs"] / peak_tflops
                                         if peak_tflops else None)
+            if name == "geometry_grid":
+                # the tally of the grid: sum of the weights per viewing
+                # direction (fixed order), what the ranks would all-reduce
+                from workloads import GRID_AZIMUTH, GRID_ZENITH
+                n_bins = GRID_ZENITH * GRID_AZIMUTH
+                grid = torch.zeros(3 * n_bins, dtype=torch.float64,
+                                   device="cuda")
+                pb.tally_segments(work.data_ptr(), events.data_ptr(), n_bins,
+                                  n // n_bins, pb.EVENT_LIMIT_ENERGY,
+                                  grid.data_ptr(), stream.cuda_stream)
+                g = grid.cpu().numpy().reshape(n_bins, 3)
+                row["grid"] = {"zenith_bins": GRID_ZENITH,
+                               "azimuth_bins": GRID_AZIMUTH,
+                               "tracks_per_bin": n // n_bins,
+                               "mean_weight_min": float((g[:, 0] / np.maximum(
+                                   g[:, 2], 1.)).min()),
+                               "mean_weight_max": float((g[:, 0] / np.maximum(
+                                   g[:, 2], 1.)).max())}
             out[name] = row
             del ctx, pristine, work, events
         except Exception as exc:  # an extra must not lose the headline line

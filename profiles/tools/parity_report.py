@@ -32,6 +32,7 @@ N_TRACKS = {
     "csda_magnet_bwd": 100000, "models_kkb_fwd": 20000,
     "models_kkb_bwd": 20000, "models_abm_fwd": 20000, "models_abm_bwd": 20000,
     "geometry_detailed": 40000, "geometry_fast": 100000,
+    "geometry_grid": 48000,
     "layers_check": 20000, "decay_randomised": 20000, "no_loss": 10000,
     "tau_ice": 100000, "above_grid": 20000, "above_grid_mixed": 100000,
     "vertex_stop": 100000, "vertex_stop_bwd": 100000, "limits_all": 40000,

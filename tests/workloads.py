@@ -161,6 +161,30 @@ def geometry_example(material, n, seed=0, phase="detailed", thickness=100.,
                                    direction=(-s, 0., -c)))
 
 
+GRID_ZENITH, GRID_AZIMUTH = 6, 8
+
+
+def geometry_grid(material, n, seed=0, thickness=100.):
+    """configs[3] as BASELINE.json states it: the detailed phase of
+    examples/pumas/geometry.c (rock + exponential air, geomagnetic field,
+    backward, straggled + mixed up to 100 GeV) over a zenith x azimuth grid of
+    GRID_ZENITH x GRID_AZIMUTH viewing directions: bin b holds the
+    n // (GRID_ZENITH * GRID_AZIMUTH) consecutive tracks [b per_bin,
+    (b + 1) per_bin) (pumas_b200_tally_segments sums their weights; ranks shard
+    the grid by bin and by track id). The remainder goes to the last bin."""
+    w = geometry_example(material, n, seed=seed, thickness=thickness)
+    n_bins = GRID_ZENITH * GRID_AZIMUTH
+    per_bin = max(1, n // n_bins)
+    b = np.minimum(np.arange(n) // per_bin, n_bins - 1)
+    zenith = np.radians(5. + 70. * ((b // GRID_AZIMUTH) + 0.5) / GRID_ZENITH)
+    azimuth = 2. * np.pi * ((b % GRID_AZIMUTH) + 0.5) / GRID_AZIMUTH
+    s, c = np.sin(zenith), np.cos(zenith)
+    w["states"]["direction"][:, 0] = -s * np.cos(azimuth)
+    w["states"]["direction"][:, 1] = -s * np.sin(azimuth)
+    w["states"]["direction"][:, 2] = -c
+    return w
+
+
 def layers_check(material, n, seed=0):
     """Three layers with exact boundary location (PUMAS_STEP_CHECK bisection,
     pumas.c:6424-6485), forward, isotropic directions, starting mid-stack."""
@@ -299,6 +323,7 @@ WORKLOADS = {
                        dict(direction=MODE_BACKWARD, scattering=MODE_MIXED)),
     "geometry_detailed": ("materials.muon", geometry_example, {}),
     "geometry_fast": ("materials.muon", geometry_example, dict(phase="fast")),
+    "geometry_grid": ("materials.muon", geometry_grid, {}),
     "layers_check": ("materials.muon", layers_check, {}),
     "decay_randomised": ("materials.muon", decay_randomised, {}),
     "no_loss": ("materials.muon", no_loss, {}),
