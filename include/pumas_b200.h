@@ -519,6 +519,24 @@ PUMAS_API enum pumas_return pumas_b200_tally(const struct pumas_state * states,
     double energy_max, int n_bins, double * out, void * scratch,
     void * cuda_stream);
 
+/* pumas.c:2797-2851. A recorder attached to `context->recorder` receives the
+ * frames of the tracks of pumas_context_transport / _transport_n (pumas.h:
+ * 432-458: every `period`-th Monte Carlo step, the events, START and STOP),
+ * in track order, as the reference's linked list of `pumas_frame` or through
+ * the `record` callback (called on the host after the batch). `frame->medium`
+ * points to a `pumas_medium` of the context (material of the layer), NULL
+ * outside. Recorded batches run the one-thread-per-track kernel twice (count,
+ * then store): a debugging tool, as in the reference. */
+PUMAS_API enum pumas_return pumas_recorder_create(
+    struct pumas_recorder ** recorder, int extra_memory);
+PUMAS_API void pumas_recorder_clear(struct pumas_recorder * recorder);
+PUMAS_API void pumas_recorder_destroy(struct pumas_recorder ** recorder);
+/* New: the frames as flat arrays, media as layer indices (bindings). Returns
+ * the number of frames of the recorder; at most `max` are copied. */
+PUMAS_API int pumas_b200_recorder_export(const struct pumas_context * context,
+    const struct pumas_recorder * recorder, long max,
+    struct pumas_state * states, int * media, int * events);
+
 /* New. pumas_context_transport_n without the wait: the batch is enqueued on
  * the context's stream and the call returns. `states`, `events`, `media` must
  * be device pointers. pumas_b200_context_synchronize waits for every batch

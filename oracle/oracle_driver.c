@@ -256,6 +256,77 @@ int oracle_transport_n(const struct pumas_physics * physics,
         return rc;
 }
 
+/*
+ * The same with a `pumas_recorder` of the given period attached to the context
+ * (single thread): the frames of track i are copied, in order, to
+ * frame_states / frame_media / frame_events starting at
+ * sum(frame_counts[0 .. i)) (at most max_frames in all; the counts are always
+ * complete). Media as layer indices, -1 for NULL.
+ */
+int oracle_transport_recorded(const struct pumas_physics * physics,
+    const struct pumas_context * settings,
+    const struct pumas_b200_geometry * geometry, uint64_t seed,
+    uint64_t offset, long n, struct pumas_state * states, int * events,
+    int period, long max_frames, struct pumas_state * frame_states,
+    int * frame_media, int * frame_events, int * frame_counts)
+{
+        if ((physics == NULL) || (settings == NULL) || (geometry == NULL) ||
+            (states == NULL) || (n < 0))
+                return PUMAS_RETURN_VALUE_ERROR;
+        oracle_set_geometry(geometry);
+        pumas_handler_cb * previous = pumas_error_handler_get();
+        pumas_error_handler_set(&oracle_silent_handler);
+
+        struct pumas_context * context = NULL;
+        struct pumas_recorder * recorder = NULL;
+        if ((pumas_context_create(&context, physics,
+                 sizeof(struct oracle_user_data)) != PUMAS_RETURN_SUCCESS) ||
+            (pumas_recorder_create(&recorder, 0) != PUMAS_RETURN_SUCCESS))
+                return PUMAS_RETURN_MEMORY_ERROR;
+        recorder->period = period;
+        context->recorder = recorder;
+        context->mode = settings->mode;
+        context->event = settings->event;
+        context->limit = settings->limit;
+        context->accuracy = settings->accuracy;
+        context->medium = &oracle_medium_cb;
+        context->random = &oracle_random;
+        struct oracle_user_data * u = context->user_data;
+        struct simulation_context * hidden =
+            (struct simulation_context *)context;
+
+        int rc = 0;
+        long i, total = 0;
+        for (i = 0; i < n; i++) {
+                pb_philox_init(&u->rng, seed, offset + (uint64_t)i);
+                hidden->randn_done = 0;
+                hidden->randn_next = 0.;
+                pumas_recorder_clear(recorder);
+                enum pumas_event event = PUMAS_EVENT_NONE;
+                const enum pumas_return r =
+                    pumas_context_transport(context, states + i, &event, NULL);
+                if ((r != PUMAS_RETURN_SUCCESS) && (rc == 0)) rc = r;
+                if (events != NULL) events[i] = (int)event;
+                const struct pumas_frame * frame;
+                int count = 0;
+                for (frame = recorder->first; frame != NULL;
+                     frame = frame->next, count++) {
+                        if (total >= max_frames) continue;
+                        frame_states[total] = frame->state;
+                        frame_media[total] = (frame->medium == NULL) ?
+                            -1 :
+                            ((struct oracle_medium *)frame->medium)->layer;
+                        frame_events[total] = (int)frame->event;
+                        total++;
+                }
+                frame_counts[i] = count;
+        }
+        pumas_recorder_destroy(&recorder);
+        pumas_context_destroy(&context);
+        pumas_error_handler_set(previous);
+        return rc;
+}
+
 /* The Philox stream as the reference's random callback sees it. */
 void oracle_philox_uniforms(uint64_t seed, uint64_t track, int n, double * out)
 {

@@ -350,6 +350,62 @@ void port_philox_uniforms(uint64_t seed, uint64_t track, int n, double * out)
         for (int i = 0; i < n; i++) out[i] = pb_philox_uniform(&g);
 }
 
+/* The recorder hooks of the engine (pb_transport.h) with a host recorder:
+ * same interface as oracle_transport_recorded (tests/test_recorder.py). */
+namespace {
+struct HostRecorder {
+        static constexpr bool enabled = true;
+        int period_;
+        std::vector<pb::State> * states;
+        std::vector<int> * media;
+        std::vector<int> * events;
+        int period() const { return period_; }
+        void frame(int medium, int event, const pb::State & state) const
+        {
+                states->push_back(state);
+                media->push_back(medium);
+                events->push_back(event);
+        }
+};
+} /* namespace */
+
+int port_transport_recorded(const void * physics,
+    const struct pumas_context * settings,
+    const struct pumas_b200_geometry * geometry, uint64_t seed, uint64_t offset,
+    long n, struct pumas_state * states, int * events, int period,
+    long max_frames, struct pumas_state * frame_states, int * frame_media,
+    int * frame_events, int * frame_counts)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        const pb::Settings cfg = settings_from(settings);
+        std::vector<pb::State> fs;
+        std::vector<int> fm, fe;
+        HostRecorder rec = { period, &fs, &fm, &fe };
+        int rc = 0;
+        long total = 0;
+        for (long i = 0; i < n; i++) {
+                PhiloxRng rng;
+                pb_philox_init(&rng.g, seed, offset + (uint64_t)i);
+                fs.clear();
+                fm.clear();
+                fe.clear();
+                unsigned int steps = 0;
+                pb::State * s = reinterpret_cast<pb::State *>(states) + i;
+                const pb::Outcome out = pb::transport_track(
+                    hp->view, cfg, *geometry, rng, *s, &steps, rec);
+                if ((out.rc != 0) && (rc == 0)) rc = out.rc;
+                if (events) events[i] = out.event;
+                frame_counts[i] = (int)fs.size();
+                for (size_t k = 0; (k < fs.size()) && (total < max_frames);
+                     k++, total++) {
+                        memcpy(&frame_states[total], &fs[k], sizeof fs[k]);
+                        frame_media[total] = fm[k];
+                        frame_events[total] = fe[k];
+                }
+        }
+        return rc;
+}
+
 /* The device logarithm of a uniform variate (tests/test_hot_math.py). */
 double port_hot_log_uniform(uint32_t w) { return pb::hot_log_uniform(w); }
 

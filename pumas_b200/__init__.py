@@ -210,6 +210,13 @@ def library():
         ctypes.c_double, ctypes.c_double, ctypes.c_int, ctypes.c_void_p,
         ctypes.c_void_p, ctypes.c_void_p]
     lib.pumas_b200_fp64_peak.argtypes = [c_double_p]
+    lib.pumas_recorder_create.argtypes = [
+        ctypes.POINTER(ctypes.c_void_p), ctypes.c_int]
+    lib.pumas_recorder_clear.argtypes = [ctypes.c_void_p]
+    lib.pumas_recorder_destroy.argtypes = [ctypes.POINTER(ctypes.c_void_p)]
+    lib.pumas_b200_recorder_export.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p]
     lib.pumas_b200_context_transport_async.argtypes = [
         ctypes.c_void_p, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
         ctypes.c_void_p]
@@ -447,6 +454,39 @@ class Context:
         _check(library().pumas_context_transport_n(
             self._ptr, n, ctypes.c_void_p(states_ptr),
             ctypes.c_void_p(events_ptr), ctypes.c_void_p(media_ptr)))
+
+    def record(self, period=1):
+        """Attach a pumas_recorder of the given sampling period (pumas.h:
+        432-458; `period` <= 0: medium changes and events only), or detach it
+        (`period=None`)."""
+        lib = library()
+        if getattr(self, "_recorder", None):
+            lib.pumas_recorder_destroy(ctypes.byref(self._recorder))
+            self._recorder = None
+            self.api.recorder = None
+        if period is None:
+            return
+        self._recorder = ctypes.c_void_p()
+        _check(lib.pumas_recorder_create(ctypes.byref(self._recorder), 0))
+        # struct pumas_recorder: first (ptr), length (int), period (int)
+        ctypes.c_int.from_address(self._recorder.value + 12).value = period
+        self.api.recorder = self._recorder.value
+
+    def frames(self, clear=True):
+        """The frames recorded so far: (states, media, events) as arrays, in
+        track order."""
+        lib = library()
+        n = lib.pumas_b200_recorder_export(
+            self._ptr, self._recorder, 0, None, None, None)
+        states = np.zeros(n, dtype=STATE_DTYPE)
+        media = np.zeros(n, dtype=np.int32)
+        events = np.zeros(n, dtype=np.int32)
+        lib.pumas_b200_recorder_export(
+            self._ptr, self._recorder, n, states.ctypes.data,
+            media.ctypes.data, events.ctypes.data)
+        if clear:
+            lib.pumas_recorder_clear(self._recorder)
+        return states, media, events
 
     def transport_async(self, n, states_ptr, events_ptr=None, media_ptr=None):
         """pumas_b200_context_transport_async: enqueue a batch (device

@@ -71,6 +71,9 @@ struct ContextImpl {
         int last_launches;
         cudaEvent_t ev0, ev1;
         int events_ready;
+        /* what `frame->medium` of a recorded frame points to: one object per
+         * layer of the geometry (material set, no locals callback) */
+        struct pumas_medium media_objects[PUMAS_B200_MAX_LAYERS];
         int device;  /* the device the buffers live on, -1: none yet */
         int pending; /* batches enqueued by transport_async, not waited for */
         int extra_memory;
@@ -374,6 +377,12 @@ const char * pumas_error_function(pumas_function_t * caller)
         NAME(pumas_context_random_load)
         NAME(pumas_context_transport)
         NAME(pumas_context_transport_n)
+        NAME(pumas_recorder_create)
+        NAME(pumas_recorder_clear)
+        NAME(pumas_recorder_destroy)
+        NAME(pumas_b200_recorder_export)
+        NAME(pumas_b200_context_transport_async)
+        NAME(pumas_b200_context_synchronize)
         NAME(pumas_b200_context_geometry_set)
         NAME(pumas_b200_context_track_offset_set)
         NAME(pumas_b200_context_stream_set)
@@ -1076,6 +1085,10 @@ enum pumas_return pumas_b200_context_geometry_set(
         const int n_layers =
             (geometry->kind == PUMAS_B200_GEOMETRY_UNIFORM) ? 1 :
                                                               geometry->n_layers;
+        for (int k = 0; (k < n_layers) && (k < PUMAS_B200_MAX_LAYERS); k++) {
+                c->media_objects[k].material = geometry->layer[k].material;
+                c->media_objects[k].locals = nullptr;
+        }
         if ((geometry->kind != PUMAS_B200_GEOMETRY_UNIFORM) &&
             (geometry->kind != PUMAS_B200_GEOMETRY_LAYERS))
                 return RAISE(pumas_b200_context_geometry_set,
@@ -1204,8 +1217,220 @@ enum pumas_return pumas_b200_context_stream_set(
         return PUMAS_RETURN_SUCCESS;
 }
 
+/* ---- recorder, pumas.c:495-505, 2796-2851, 7738-7780 ------------------------ */
+namespace {
+
+struct FrameStack {
+        FrameStack * next;
+        int used, capacity;
+        struct pumas_frame frames[1];
+};
+
+struct RecorderImpl {
+        struct pumas_recorder api;
+        struct pumas_frame * last;
+        FrameStack * stack;
+        double data[1]; /* user memory follows */
+};
+
+/* record_state, pumas.c:7738-7780 (frames in blocks of ~4 KB) */
+void recorder_append(struct pumas_context * context,
+    struct pumas_recorder * recorder, struct pumas_medium * medium,
+    enum pumas_event event, struct pumas_state * state)
+{
+        if (recorder->record != nullptr) {
+                recorder->record(context, state, medium, event);
+                return;
+        }
+        RecorderImpl * rec = reinterpret_cast<RecorderImpl *>(recorder);
+        FrameStack * stack = rec->stack;
+        if ((stack == nullptr) || (stack->used >= stack->capacity)) {
+                const int capacity = 32;
+                stack = static_cast<FrameStack *>(g_allocate(sizeof(FrameStack) +
+                    (capacity - 1) * sizeof(struct pumas_frame)));
+                if (stack == nullptr) return;
+                stack->used = 0;
+                stack->capacity = capacity;
+                stack->next = rec->stack;
+                rec->stack = stack;
+        }
+        struct pumas_frame * frame = stack->frames + stack->used++;
+        if (recorder->first == nullptr)
+                recorder->first = frame;
+        else
+                rec->last->next = frame;
+        rec->last = frame;
+        frame->next = nullptr;
+        frame->medium = medium;
+        frame->event = event;
+        memcpy(&frame->state, state, sizeof *state);
+        recorder->length++;
+}
+
+} /* namespace */
+
+extern "C" {
+
+enum pumas_return pumas_recorder_create(
+    struct pumas_recorder ** recorder_, int extra_memory)
+{
+        if (recorder_ == nullptr)
+                return RAISE(pumas_recorder_create, PUMAS_RETURN_VALUE_ERROR,
+                    "a NULL recorder pointer was provided");
+        *recorder_ = nullptr;
+        if (extra_memory < 0) extra_memory = 0;
+        RecorderImpl * rec = static_cast<RecorderImpl *>(
+            g_allocate(sizeof(RecorderImpl) + (size_t)extra_memory));
+        if (rec == nullptr)
+                return RAISE(pumas_recorder_create, PUMAS_RETURN_MEMORY_ERROR,
+                    "could not allocate memory");
+        rec->api.period = 1;
+        rec->api.record = nullptr;
+        rec->api.length = 0;
+        rec->api.first = nullptr;
+        rec->api.user_data = (extra_memory > 0) ? rec->data : nullptr;
+        rec->last = nullptr;
+        rec->stack = nullptr;
+        *recorder_ = &rec->api;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+void pumas_recorder_clear(struct pumas_recorder * recorder)
+{
+        if (recorder == nullptr) return;
+        RecorderImpl * rec = reinterpret_cast<RecorderImpl *>(recorder);
+        while (rec->stack != nullptr) {
+                FrameStack * next = rec->stack->next;
+                g_deallocate(rec->stack);
+                rec->stack = next;
+        }
+        rec->last = nullptr;
+        recorder->first = nullptr;
+        recorder->length = 0;
+}
+
+void pumas_recorder_destroy(struct pumas_recorder ** recorder)
+{
+        if ((recorder == nullptr) || (*recorder == nullptr)) return;
+        pumas_recorder_clear(*recorder);
+        g_deallocate(*recorder);
+        *recorder = nullptr;
+}
+
+/* New: the frames of a recorder as flat arrays (bindings): up to `max` frames
+ * are copied; media as layer indices of the context's geometry (-1 = none).
+ * Returns the number of frames of the recorder. */
+int pumas_b200_recorder_export(const struct pumas_context * context,
+    const struct pumas_recorder * recorder, long max,
+    struct pumas_state * states, int * media, int * events)
+{
+        if ((context == nullptr) || (recorder == nullptr)) return 0;
+        const ContextImpl * c = reinterpret_cast<const ContextImpl *>(context);
+        long k = 0;
+        for (const struct pumas_frame * f = recorder->first; f != nullptr;
+             f = f->next, k++) {
+                if (k >= max) continue;
+                if (states != nullptr) states[k] = f->state;
+                if (media != nullptr)
+                        media[k] = (f->medium == nullptr) ?
+                            -1 :
+                            (int)(f->medium - c->media_objects);
+                if (events != nullptr) events[k] = (int)f->event;
+        }
+        return (int)k;
+}
+
+} /* extern "C" */
+
 /* ---- transport -------------------------------------------------------------- */
 namespace {
+
+/* A batch with a recorder attached to the context. The states at `d_states`
+ * are transported in place; the frames are handed to the recorder in track
+ * order (record_state, pumas.c:7738). */
+enum pumas_return transport_recorded(pumas_function_t * caller, ContextImpl * c,
+    const pb::Physics & d_view, const pb::Physics & host_view,
+    const pb::Settings & cfg, long n, pb::State * d_states, int * d_events,
+    int * d_media, cudaStream_t stream)
+{
+        (void)host_view;
+#define RAISE_R(rc, ...) raise(caller, rc, __FILE__, __LINE__, __VA_ARGS__)
+        struct pumas_context * context = &c->api;
+        struct pumas_recorder * recorder = context->recorder;
+        pb::State * d_copy = nullptr;
+        int * d_counts = nullptr;
+        long * d_first = nullptr;
+        pb::DeviceFrame * d_frames = nullptr;
+        std::vector<int> counts(n);
+        std::vector<long> first(n + 1, 0);
+        std::vector<pb::DeviceFrame> frames;
+        cudaError_t e = cudaMalloc(&d_copy, n * sizeof(pb::State));
+        if (e == cudaSuccess) e = cudaMalloc(&d_counts, n * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&d_first, (n + 1) * sizeof(long));
+        /* pass 1: count (on a copy of the inputs) */
+        if (e == cudaSuccess)
+                e = cudaMemcpyAsync(d_copy, d_states, n * sizeof(pb::State),
+                    cudaMemcpyDeviceToDevice, stream);
+        if (e == cudaSuccess)
+                e = cudaMemsetAsync(c->d_status, 0, sizeof(int), stream);
+        if (e == cudaSuccess)
+                e = pb::launch_transport_recorded(d_view, cfg, c->geometry,
+                    (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_copy,
+                    nullptr, nullptr, c->d_status, nullptr, nullptr,
+                    recorder->period, nullptr, nullptr, d_counts, stream);
+        if (e == cudaSuccess)
+                e = cudaMemcpyAsync(counts.data(), d_counts, n * sizeof(int),
+                    cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e == cudaSuccess) {
+                for (long i = 0; i < n; i++) first[i + 1] = first[i] + counts[i];
+                e = cudaMalloc(&d_frames,
+                    (first[n] > 0 ? first[n] : 1) * sizeof(pb::DeviceFrame));
+        }
+        /* pass 2: record, on the caller's states */
+        if (e == cudaSuccess)
+                e = cudaMemcpyAsync(d_first, first.data(),
+                    (n + 1) * sizeof(long), cudaMemcpyHostToDevice, stream);
+        if (e == cudaSuccess)
+                e = cudaMemsetAsync(c->d_status, 0, sizeof(int), stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev0, stream);
+        if (e == cudaSuccess)
+                e = pb::launch_transport_recorded(d_view, cfg, c->geometry,
+                    (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_states,
+                    d_events, d_media, c->d_status, c->d_random, c->d_steps,
+                    recorder->period, d_frames, d_first, d_counts, stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->ev1, stream);
+        if (e == cudaSuccess) {
+                frames.resize(first[n]);
+                if (first[n] > 0)
+                        e = cudaMemcpyAsync(frames.data(), d_frames,
+                            first[n] * sizeof(pb::DeviceFrame),
+                            cudaMemcpyDeviceToHost, stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (d_copy) cudaFree(d_copy);
+        if (d_counts) cudaFree(d_counts);
+        if (d_first) cudaFree(d_first);
+        if (d_frames) cudaFree(d_frames);
+        if (e != cudaSuccess)
+                return RAISE_R(PUMAS_RETURN_INTERNAL_ERROR, "CUDA error (%s)",
+                    cudaGetErrorString(e));
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        c->last_ms = ms;
+        for (long k = 0; k < first[n]; k++) {
+                pb::DeviceFrame & f = frames[k];
+                struct pumas_medium * medium = ((f.medium < 0) ||
+                    (f.medium >= PUMAS_B200_MAX_LAYERS)) ?
+                    nullptr :
+                    &c->media_objects[f.medium];
+                recorder_append(context, recorder, medium,
+                    (enum pumas_event)f.event,
+                    reinterpret_cast<struct pumas_state *>(&f.state));
+        }
+        return PUMAS_RETURN_SUCCESS;
+#undef RAISE_R
+}
 
 /* One batch, for the public entry point `caller` (errors are attributed to
  * it, as the reference does). `async`: enqueue on the context's stream and
@@ -1237,10 +1462,9 @@ enum pumas_return transport_batch(pumas_function_t * caller,
                             "pumas_b200_context_geometry_set");
                 return RAISE_C(PUMAS_RETURN_MEDIUM_ERROR, "no medium specified");
         }
-        if (context->recorder != nullptr)
+        if ((context->recorder != nullptr) && async)
                 return RAISE_C(PUMAS_RETURN_VALUE_ERROR,
-                    "context->recorder is a host object: the device kernels "
-                    "do not record frames (not implemented)");
+                    "a recorder needs the synchronous entry points");
 
         /* Configuration checks, pumas.c:3152-3177. */
         const pb::Settings cfg = settings_from(context);
@@ -1321,6 +1545,43 @@ enum pumas_return transport_batch(pumas_function_t * caller,
         if (!states_on_device)
                 e = cudaMemcpyAsync(d_states, states, n * sizeof(pb::State),
                     cudaMemcpyHostToDevice, stream);
+        if ((e == cudaSuccess) && (context->recorder != nullptr)) {
+                /* the recorder (pumas.h:432-458): two passes of the
+                 * recording kernel over the same inputs and streams, the
+                 * first counts the frames of every track, the second stores
+                 * them; then the frames go to the recorder in track order */
+                const enum pumas_return rr = transport_recorded(caller, c, d_view,
+                    physics->host.view, cfg, n, d_states, d_events, d_media,
+                    stream);
+                if (rr != PUMAS_RETURN_SUCCESS) return rr;
+                int status = 0;
+                if (!states_on_device)
+                        e = cudaMemcpyAsync(states, d_states,
+                            n * sizeof(pb::State), cudaMemcpyDeviceToHost,
+                            stream);
+                if ((e == cudaSuccess) && (events != nullptr) &&
+                    !events_on_device)
+                        e = cudaMemcpyAsync(events, d_events, n * sizeof(int),
+                            cudaMemcpyDeviceToHost, stream);
+                if ((e == cudaSuccess) && (media != nullptr) &&
+                    !media_on_device)
+                        e = cudaMemcpyAsync(media, d_media, 2 * n * sizeof(int),
+                            cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess)
+                        e = cudaMemcpyAsync(&status, c->d_status, sizeof(int),
+                            cudaMemcpyDeviceToHost, stream);
+                if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+                if (e != cudaSuccess)
+                        return RAISE_C(PUMAS_RETURN_INTERNAL_ERROR,
+                            "CUDA error (%s)", cudaGetErrorString(e));
+                c->last_launches = 2;
+                c->last_n = n;
+                c->track_offset += (unsigned long long)n;
+                if (status != 0)
+                        return RAISE_C((enum pumas_return)status, "%s",
+                            return_text(status));
+                return PUMAS_RETURN_SUCCESS;
+        }
         if ((e == cudaSuccess) && !c->pending)
                 e = cudaMemsetAsync(c->d_status, 0, sizeof(int), stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev0, stream);

@@ -46,6 +46,84 @@ __global__ void __launch_bounds__(TRANSPORT_BLOCK)
         if (n_steps != nullptr) n_steps[i] = steps;
 }
 
+/* ------------------------------------------------------------------------
+ * The recorder on the device (pumas.h:432-458; hooks of pb_transport.h): one
+ * thread per track, the general code instantiated on a recorder that appends
+ * frames to the track's segment of a buffer in HBM. Contexts without a
+ * recorder never run this kernel: recording costs them nothing.
+ * ------------------------------------------------------------------------ */
+struct DeviceRecorder {
+        static constexpr bool enabled = true;
+        DeviceFrame * frames; /* this track's segment, or NULL */
+        int capacity;
+        int * count;
+        int period_;
+        __device__ __forceinline__ int period() const { return period_; }
+        __device__ __forceinline__ void frame(
+            int medium, int event, const State & state) const
+        {
+                const int k = (*count)++;
+                if ((frames != nullptr) && (k < capacity)) {
+                        frames[k].state = state;
+                        frames[k].medium = medium;
+                        frames[k].event = event;
+                }
+        }
+};
+
+__global__ void __launch_bounds__(TRANSPORT_BLOCK)
+    transport_record_kernel(const Physics p, const Settings cfg,
+        const Geometry geo, const uint64_t seed, const uint64_t offset,
+        const long n, State * __restrict__ states, int * __restrict__ events,
+        int * __restrict__ media, int * __restrict__ status,
+        unsigned int * __restrict__ n_random,
+        unsigned int * __restrict__ n_steps, int period,
+        DeviceFrame * __restrict__ frames, const long * __restrict__ first,
+        int * __restrict__ counts)
+{
+        const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+        if (i >= n) return;
+
+        State state = states[i];
+        DeviceRng rng;
+        rng.init(seed, offset + (uint64_t)i);
+        unsigned int steps = 0;
+        int count = 0;
+        DeviceRecorder rec;
+        rec.frames = (frames != nullptr) ? frames + first[i] : nullptr;
+        rec.capacity = (frames != nullptr) ? (int)(first[i + 1] - first[i]) : 0;
+        rec.count = &count;
+        rec.period_ = period;
+        const Outcome out =
+            transport_track(p, cfg, geo, rng, state, &steps, rec);
+        states[i] = state;
+        counts[i] = count;
+        if (events != nullptr) events[i] = out.event;
+        if (media != nullptr) {
+                media[2 * i] = out.medium[0];
+                media[2 * i + 1] = out.medium[1];
+        }
+        if (out.rc != RETURN_SUCCESS) atomicCAS(status, 0, out.rc);
+        if (n_random != nullptr) n_random[i] = rng.count;
+        if (n_steps != nullptr) n_steps[i] = steps;
+}
+
+cudaError_t launch_transport_recorded(const Physics & p, const Settings & cfg,
+    const Geometry & geo, uint64_t seed, uint64_t offset, long n,
+    State * states, int * events, int * media, int * status,
+    unsigned int * n_random, unsigned int * n_steps, int period,
+    DeviceFrame * frames, const long * first, int * counts,
+    cudaStream_t stream)
+{
+        if (n <= 0) return cudaSuccess;
+        last_launch_count() = 1;
+        const long blocks = (n + TRANSPORT_BLOCK - 1) / TRANSPORT_BLOCK;
+        transport_record_kernel<<<(unsigned int)blocks, TRANSPORT_BLOCK, 0,
+            stream>>>(p, cfg, geo, seed, offset, n, states, events, media,
+            status, n_random, n_steps, period, frames, first, counts);
+        return cudaGetLastError();
+}
+
 PB_SPECIALISATION(launch_spec_straggled_mixed_forward);
 PB_SPECIALISATION(launch_spec_straggled_mixed_backward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_forward);

@@ -35,6 +35,26 @@ cudaError_t transport_workspace_bytes(size_t * bytes);
  * the DEL CTAs are prepared by resident_offload_init). */
 int transport_last_launches();
 
+/* A recorded frame on the device: struct pumas_frame (pumas.h:380-392) with the
+ * medium as a layer index (-1 = none). */
+struct DeviceFrame {
+        State state;
+        int medium;
+        int event;
+};
+
+/* Transport n tracks with a recorder of the given period (pumas.h:432-458),
+ * one thread per track on the general code. Track i appends its frames at
+ * frames[first[i] ...] (at most first[i + 1] - first[i] of them are stored)
+ * and writes how many it produced to counts[i]. `frames` / `first` may be
+ * NULL: count only. */
+cudaError_t launch_transport_recorded(const Physics & p, const Settings & cfg,
+    const Geometry & geo, uint64_t seed, uint64_t offset, long n,
+    State * states, int * events, int * media, int * status,
+    unsigned int * n_random, unsigned int * n_steps, int period,
+    DeviceFrame * frames, const long * first, int * counts,
+    cudaStream_t stream);
+
 /* Transport n tracks. `p` is the device view of the physics tables and
  * `host_view` the host one (per launch constants are read from it). All
  * other pointers are device pointers; `status` receives the

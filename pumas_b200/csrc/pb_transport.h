@@ -39,6 +39,19 @@ typedef __float128 CoulombReal;
 typedef long double CoulombReal;
 #endif
 
+/* Recorder hooks (record_state, pumas.c:7738-7780, called at pumas.c:3191,
+ * 4798, 4946, 5230, 5326, 5368, 5385, 5466, 5509). The engine is a template
+ * on the recorder type; the default records nothing and compiles away (zero
+ * cost when `context->recorder == NULL`). `medium` is a layer index, -1 for
+ * the reference's NULL medium. */
+constexpr int EVENT_START = 4096;
+constexpr int EVENT_STOP = 8192;
+struct NoRecorder {
+        static constexpr bool enabled = false;
+        PB_FN int period() const { return 0; }
+        PB_FN void frame(int, int, const State &) const {}
+};
+
 /* Hidden stepping state, pumas.c:426-477. */
 struct Track {
         double lifetime;
@@ -1124,9 +1137,10 @@ PB_FN void stepping_finish(const Cfg & cfg, State & state)
 /* pumas.c:5210-5273. Returns PHASE_STEP, or PHASE_DONE when the track stops
  * before its first step (then `*final` tells whether the final protections
  * apply: the reference returns early, skipping them, at :5250-5273). */
-template <class Cfg, class Geo, class Rng>
+template <class Cfg, class Geo, class Rng, class Rec = NoRecorder>
 PB_FN int stepping_begin(const Physics & p, const Cfg & cfg,
-    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp,
+    const Rec & rec = Rec())
 {
         lp.material = geo_material(geo, lp.medium);
         const int scheme = cfg.energy_loss;
@@ -1134,6 +1148,9 @@ PB_FN int stepping_begin(const Physics & p, const Cfg & cfg,
         lp.first = 1;
 
         trk.step_event = EVENT_NONE;
+        /* the start of the track, pumas.c:5229-5231 */
+        if (Rec::enabled)
+                rec.frame(lp.medium, trk.step_event | EVENT_START, state);
         lp.ti = state.time;
         lp.wi = state.weight;
         lp.Xi = state.grammage;
@@ -1172,16 +1189,29 @@ PB_FN int stepping_begin(const Physics & p, const Cfg & cfg,
         trk.step_invlb1 = 0;
         transport_limit(p, cfg, trk, rng, state, lp.material, lp.Xi, lp.Xf,
             &lp.grammage_max);
+        /* (an early return of the reference, pumas.c:5273: no STOP frame) */
         if (trk.step_event) return PHASE_DONE;
         return PHASE_STEP;
 }
 
 /* pumas.c:5404-5416 and 5476-5488: refresh the locals after a vertex, update
  * the initial conditions and draw the next limits. */
-template <class Cfg, class Geo, class Rng>
+/* The end of the stepping loop: final protections then the STOP frame,
+ * pumas.c:5492-5510. */
+template <class Cfg, class Rec>
+PB_FN int stepping_stop(const Cfg & cfg, const Track & trk, State & state,
+    const Loop & lp, const Rec & rec)
+{
+        stepping_finish(cfg, state);
+        if (Rec::enabled)
+                rec.frame(lp.medium, trk.step_event | EVENT_STOP, state);
+        return PHASE_DONE;
+}
+
+template <class Cfg, class Geo, class Rng, class Rec = NoRecorder>
 PB_FN int stepping_rearm(const Physics & p, const Cfg & cfg,
     const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp,
-    bool after_vertex)
+    bool after_vertex, const Rec & rec = Rec())
 {
         if (geo_has_locals(geo) && after_vertex && (lp.step_max_locals > 0.)) {
                 lp.step_max_locals = set_locals(
@@ -1202,19 +1232,17 @@ PB_FN int stepping_rearm(const Physics & p, const Cfg & cfg,
         }
         transport_limit(p, cfg, trk, rng, state, lp.material, lp.Xi, lp.Xf,
             &lp.grammage_max);
-        if (trk.step_event) {
-                stepping_finish(cfg, state);
-                return PHASE_DONE;
-        }
+        if (trk.step_event) return stepping_stop(cfg, trk, state, lp, rec);
         return PHASE_STEP;
 }
 
 /* One iteration of the stepping loop, pumas.c:5277-5335 and, for a change of
  * medium, 5417-5467 + re-arm. */
-template <class Cfg, class Geo, class Rng, class Sync = NoSync>
+template <class Cfg, class Geo, class Rng, class Sync = NoSync,
+    class Rec = NoRecorder>
 PB_FN int stepping_step(const Physics & p, const Cfg & cfg,
     const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp,
-    const Sync & sync = Sync())
+    const Sync & sync = Sync(), const Rec & rec = Rec())
 {
         if (!lp.first) {
                 lp.step_max_type = medium_locate(geo, cfg.direction, state,
@@ -1231,7 +1259,12 @@ PB_FN int stepping_step(const Physics & p, const Cfg & cfg,
                 return PHASE_DONE; /* error: no final protection (:5293) */
         lp.first = 0;
 
-        if (!trk.step_event) return PHASE_STEP;
+        /* sampled steps, pumas.c:5296-5304 (step_index = steps so far + 1) */
+        bool record_step = false;
+        if (Rec::enabled && (rec.period() > 0))
+                record_step =
+                    ((trk.n_steps + 1u) % (unsigned int)rec.period()) == 0u;
+        if (!trk.step_event && !record_step) return PHASE_STEP;
 
         /* Weight update at a boundary or hard loss, pumas.c:5309-5321. */
         const int scheme = cfg.energy_loss;
@@ -1247,10 +1280,14 @@ PB_FN int stepping_step(const Physics & p, const Cfg & cfg,
                 state.weight = lp.wi * xexp(-fabs(state.time - lp.ti) / p.ctau);
         }
 
+        if (!trk.step_event) {
+                /* a sampled step, pumas.c:5324-5327 */
+                if (Rec::enabled) rec.frame(lp.medium, trk.step_event, state);
+                return PHASE_STEP;
+        }
         if (trk.step_event &
             (EVENT_LIMIT | EVENT_WEIGHT | EVENT_VERTEX_DECAY)) {
-                stepping_finish(cfg, state);
-                return PHASE_DONE;
+                return stepping_stop(cfg, trk, state, lp, rec);
         } else if (trk.step_event & EVENT_VERTEX_DEL) {
                 return PHASE_DEL;
         } else if (trk.step_event & EVENT_VERTEX_COULOMB) {
@@ -1263,10 +1300,8 @@ PB_FN int stepping_step(const Physics & p, const Cfg & cfg,
                 return PHASE_DONE;
         }
         lp.medium = new_medium;
-        if ((lp.medium < 0) || (cfg.event & EVENT_MEDIUM)) {
-                stepping_finish(cfg, state);
-                return PHASE_DONE;
-        }
+        if ((lp.medium < 0) || (cfg.event & EVENT_MEDIUM))
+                return stepping_stop(cfg, trk, state, lp, rec);
         lp.material = geo_material(geo, lp.medium);
         lp.locals.density = 0.;
         lp.locals.magnet[0] = lp.locals.magnet[1] = lp.locals.magnet[2] = 0.;
@@ -1285,35 +1320,51 @@ PB_FN int stepping_step(const Physics & p, const Cfg & cfg,
             0.;
         trk.step_first = 1;
         trk.step_invlb1 = 0;
-        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, false);
+        /* the change of medium, pumas.c:5464-5467 */
+        if (Rec::enabled && !(cfg.event & EVENT_MEDIUM))
+                rec.frame(lp.medium, trk.step_event, state);
+        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, false, rec);
 }
 
 /* A hard inelastic event, pumas.c:5340-5392 then re-arm. */
-template <class Cfg, class Geo, class Rng>
+template <class Cfg, class Geo, class Rng, class Rec = NoRecorder>
 PB_FN int stepping_del(const Physics & p, const Cfg & cfg,
-    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp,
+    const Rec & rec = Rec())
 {
+        /* the pre-vertex point, pumas.c:5343-5375 */
+        const bool record = Rec::enabled && (rec.period() > 0);
+        const double ki = state.energy;
+        const double ui[3] = { state.direction[0], state.direction[1],
+                state.direction[2] };
         transport_do_del(p, cfg, trk, rng, state, lp.material);
-        if ((cfg.event & trk.step_event) || trk.step_event == EVENT_WEIGHT) {
-                stepping_finish(cfg, state);
-                return PHASE_DONE;
+        if (record) {
+                State pre = state;
+                pre.energy = ki;
+                pre.direction[0] = ui[0];
+                pre.direction[1] = ui[1];
+                pre.direction[2] = ui[2];
+                rec.frame(lp.medium, trk.step_event, pre);
         }
+        if ((cfg.event & trk.step_event) || trk.step_event == EVENT_WEIGHT)
+                return stepping_stop(cfg, trk, state, lp, rec);
+        /* the post-vertex point, pumas.c:5383-5386 */
+        if (record) rec.frame(lp.medium, EVENT_NONE, state);
         trk.step_first = 1;
         trk.step_invlb1 = 0;
-        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, true);
+        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, true, rec);
 }
 
 /* A hard elastic event, pumas.c:5393-5402 then re-arm. */
-template <class Cfg, class Geo, class Rng>
+template <class Cfg, class Geo, class Rng, class Rec = NoRecorder>
 PB_FN int stepping_ehs(const Physics & p, const Cfg & cfg,
-    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp)
+    const Geo & geo, Track & trk, Rng & rng, State & state, Loop & lp,
+    const Rec & rec = Rec())
 {
         transport_do_ehs(p, cfg, rng, state, lp.material, trk.iK);
-        if (cfg.event & trk.step_event) {
-                stepping_finish(cfg, state);
-                return PHASE_DONE;
-        }
-        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, true);
+        if (cfg.event & trk.step_event)
+                return stepping_stop(cfg, trk, state, lp, rec);
+        return stepping_rearm(p, cfg, geo, trk, rng, state, lp, true, rec);
 }
 
 /* Total magnetic transport within the CSDA, uniform medium: the Larmor
@@ -1473,10 +1524,10 @@ PB_NOINLINE int transport_csda_deflect(const Physics & p, int direction_mode,
 
 /* Closed form CSDA in a uniform medium. pumas.c:4777-4949. `*rc` receives the
  * return code of the magnetic deflection (pumas.c:4929-4933). */
-template <class Cfg, class Geo>
+template <class Cfg, class Geo, class Rec = NoRecorder>
 PB_FN int transport_with_csda(const Physics & p, const Cfg & cfg,
     const Geo & geo, const Track & trk, State & state, int medium,
-    const Locals & locals, int * rc)
+    const Locals & locals, int * rc, const Rec & rec = Rec())
 {
         const int material = geo_material(geo, medium);
         const double density = locals.density;
@@ -1487,6 +1538,8 @@ PB_FN int transport_with_csda(const Physics & p, const Cfg & cfg,
         const double Ti = cel_proper_time(p, MODE_CSDA, material, ki);
 
         int event = EVENT_NONE;
+        /* the start of the track, pumas.c:4797-4798 */
+        if (Rec::enabled) rec.frame(medium, event | EVENT_START, state);
         double xB;
         if (cfg.event & EVENT_LIMIT_GRAMMAGE) {
                 xB = cfg.limit_grammage - state.grammage;
@@ -1619,6 +1672,8 @@ PB_FN int transport_with_csda(const Physics & p, const Cfg & cfg,
                 state.position[2] += path * state.direction[2];
         }
 
+        /* the end of the track, pumas.c:4945-4946 */
+        if (Rec::enabled) rec.frame(medium, event | EVENT_STOP, state);
         return event;
 }
 
@@ -1649,10 +1704,10 @@ PB_FN int settings_check(const Physics & p, const Cfg & cfg)
  * (the track is then over) or the prologue of the stepping. Returns the phase
  * of the track; `out` holds rc, the first medium and, when PHASE_DONE is
  * returned, the end event and last medium. */
-template <class Cfg, class Geo, class Rng>
+template <class Cfg, class Geo, class Rng, class Rec = NoRecorder>
 PB_FN int track_begin(const Physics & p, const Cfg & cfg,
     const Geo & geo, Rng & rng, State & state, Track & trk, Loop & lp,
-    Outcome & out)
+    Outcome & out, const Rec & rec = Rec())
 {
         out.rc = RETURN_SUCCESS;
         out.event = EVENT_NONE;
@@ -1692,6 +1747,10 @@ PB_FN int track_begin(const Physics & p, const Cfg & cfg,
         out.medium[1] = -1;
         if (medium < 0) {
                 out.event = EVENT_MEDIUM;
+                /* pumas.c:3190-3194 */
+                if (Rec::enabled)
+                        rec.frame(-1,
+                            EVENT_MEDIUM | EVENT_START | EVENT_STOP, state);
                 return PHASE_DONE;
         } else if ((step_max_medium > 0.) && (step_max_type == STEP_CHECK))
                 step_max_medium += 0.5 * STEP_MIN;
@@ -1729,7 +1788,7 @@ PB_FN int track_begin(const Physics & p, const Cfg & cfg,
         lp.medium = medium;
         if (!do_stepping) {
                 out.event = transport_with_csda(
-                    p, cfg, geo, trk, state, medium, locals, &out.rc);
+                    p, cfg, geo, trk, state, medium, locals, &out.rc, rec);
                 out.medium[1] = medium;
                 return PHASE_DONE;
         }
@@ -1737,7 +1796,8 @@ PB_FN int track_begin(const Physics & p, const Cfg & cfg,
         lp.step_max_medium = step_max_medium;
         lp.step_max_type = step_max_type;
         lp.step_max_locals = step_max_locals;
-        const int phase = stepping_begin(p, cfg, geo, trk, rng, state, lp);
+        const int phase =
+            stepping_begin(p, cfg, geo, trk, rng, state, lp, rec);
         if (phase == PHASE_DONE) {
                 out.event = trk.step_event;
                 out.medium[1] = lp.medium;
@@ -1756,25 +1816,26 @@ PB_FN void track_end(const Track & trk, const Loop & lp, Outcome & out)
 
 /* pumas_context_transport for one track run to completion (CPU build and the
  * reference kernel): the phases chained in sequence. */
-template <class Cfg, class Geo, class Rng>
+template <class Cfg, class Geo, class Rng, class Rec = NoRecorder>
 PB_FN Outcome transport_track(const Physics & p, const Cfg & cfg,
-    const Geo & geo, Rng & rng, State & state, unsigned int * n_steps)
+    const Geo & geo, Rng & rng, State & state, unsigned int * n_steps,
+    const Rec & rec = Rec())
 {
         Outcome out;
         Track trk;
         Loop lp;
-        int phase = track_begin(p, cfg, geo, rng, state, trk, lp, out);
+        int phase = track_begin(p, cfg, geo, rng, state, trk, lp, out, rec);
         if (phase != PHASE_DONE) {
                 while (phase != PHASE_DONE) {
                         if (phase == PHASE_STEP)
-                                phase = stepping_step(
-                                    p, cfg, geo, trk, rng, state, lp);
+                                phase = stepping_step(p, cfg, geo, trk, rng,
+                                    state, lp, NoSync(), rec);
                         else if (phase == PHASE_EHS)
                                 phase = stepping_ehs(
-                                    p, cfg, geo, trk, rng, state, lp);
+                                    p, cfg, geo, trk, rng, state, lp, rec);
                         else
                                 phase = stepping_del(
-                                    p, cfg, geo, trk, rng, state, lp);
+                                    p, cfg, geo, trk, rng, state, lp, rec);
                 }
                 track_end(trk, lp, out);
         }

@@ -151,6 +151,32 @@ class Oracle:
         p = self.lib.oracle_table(self.physics, name.encode(), ctypes.byref(n))
         return np.ctypeslib.as_array(p, shape=(n.value,)).copy()
 
+    def transport_recorded(self, settings, geometry, states, period, seed=0,
+                           offset=0, max_frames=1 << 22):
+        """The reference with a pumas_recorder attached. Returns (states,
+        events, frame_states, frame_media, frame_events, counts, rc)."""
+        from pumas_b200 import STATE_DTYPE
+        s = np.ascontiguousarray(states.copy())
+        n = len(s)
+        events = np.zeros(n, dtype=np.int32)
+        fs = np.zeros(max_frames, dtype=STATE_DTYPE)
+        fm = np.zeros(max_frames, dtype=np.int32)
+        fe = np.zeros(max_frames, dtype=np.int32)
+        counts = np.zeros(n, dtype=np.int32)
+        f = self.lib.oracle_transport_recorded
+        f.argtypes = [
+            ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+            ctypes.c_uint64, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_int, ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_void_p, ctypes.c_void_p]
+        rc = f(self.physics, ctypes.byref(settings), ctypes.byref(geometry),
+               seed, offset, n, s.ctypes.data, events.ctypes.data, period,
+               max_frames, fs.ctypes.data, fm.ctypes.data, fe.ctypes.data,
+               counts.ctypes.data)
+        total = int(counts.sum())
+        assert total <= max_frames, "more frames than max_frames"
+        return s, events, fs[:total], fm[:total], fe[:total], counts, rc
+
     def transport(self, settings, geometry, states, seed=0, offset=0,
                   threads=1):
         """Returns (states, events, media, n_random, rc, seconds)."""
