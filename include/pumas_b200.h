@@ -429,6 +429,33 @@ PUMAS_API enum pumas_return pumas_context_random_load(
 PUMAS_API enum pumas_return pumas_b200_context_geometry_set(
     struct pumas_context * context,
     const struct pumas_b200_geometry * geometry);
+/* New. `__device__` medium / locals functions (struct pumas_b200_callbacks,
+ * pumas_b200_geometry.h): the device form of `context->medium` (pumas.h:641,
+ * 509-511) and of `pumas_medium::locals` (pumas.h:348-349, 466-480) for
+ * geometries the descriptor does not cover. The table is copied; it takes
+ * precedence over a descriptor; NULL removes it. The functions must belong to
+ * the device link unit of the kernels: the built-in planar client below, or
+ * user code built in with `python -m pumas_b200.build --user file.cu`
+ * (INTEGRATION.md section 6). */
+PUMAS_API enum pumas_return pumas_b200_context_callbacks_set(
+    struct pumas_context * context,
+    const struct pumas_b200_callbacks * callbacks);
+/* New. The planar media of `geometry` behind the callback interface (the
+ * library's own client of it): fills `callbacks`, whose user_data is a device
+ * copy of the descriptor, released by pumas_b200_planar_callbacks_free. */
+PUMAS_API enum pumas_return pumas_b200_planar_callbacks(
+    const struct pumas_b200_geometry * geometry,
+    struct pumas_b200_callbacks * callbacks);
+PUMAS_API void pumas_b200_planar_callbacks_free(
+    struct pumas_b200_callbacks * callbacks);
+/* New. The `__device__` counterpart of a DCS model registered with
+ * pumas_dcs_register (pumas.h:2150-2167): same signature, same value, as a
+ * device function pointer of the device link unit of the kernels (user code
+ * built in with `python -m pumas_b200.build --user file.cu`). A physics whose
+ * tables were made with a user model (the dump names it) loads once the model
+ * is registered and transports once its device function is. */
+PUMAS_API enum pumas_return pumas_b200_dcs_register_device(
+    enum pumas_process process, const char * model, pumas_dcs_t * device_dcs);
 /* New. Id of the first track of the next batch: track i of a batch draws from
  * the Philox stream (seed, offset + i). Lets ranks/batches own disjoint,
  * reproducible id ranges. */

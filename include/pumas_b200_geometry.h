@@ -56,6 +56,43 @@ struct pumas_b200_geometry {
         struct pumas_b200_layer layer[PUMAS_B200_MAX_LAYERS];
 };
 
+/* ------------------------------------------------------------------------
+ * Device callbacks: the counterparts of `pumas_medium_cb` (pumas.h:509-511)
+ * and `pumas_locals_cb` (pumas.h:348-349) as `__device__` functions, for
+ * geometries the descriptors above do not cover. The pointers are DEVICE
+ * function pointers (read from a `__device__` variable with
+ * cudaMemcpyFromSymbol); they are only callable by kernels of the same device
+ * link unit: the built-in clients of the library (pumas_b200_planar_callbacks),
+ * or user functions linked with the relocatable build of the kernels
+ * (libpumas_b200_rdc.a).
+ * ------------------------------------------------------------------------ */
+struct pumas_state;
+
+/* Locate `state` and / or propose a step. `medium`, when not NULL, receives
+ * the index of the medium (0 .. n_media - 1; -1 outside); `step`, when not
+ * NULL, the proposed stepping distance [m] along the motion (<= 0: no
+ * boundary). `backward` != 0: the particle moves opposite to state->direction.
+ * Returns an enum pumas_step (PUMAS_STEP_CHECK = 0, PUMAS_STEP_RAW = 1). */
+typedef int pumas_b200_medium_fn(const void * user_data,
+    const struct pumas_state * state, int backward, int * medium,
+    double * step);
+
+/* Local properties of medium `medium` at `state`: density [kg/m^3] (<= 0
+ * selects the material's default) and magnetic field [T]. Returns the size of
+ * the inhomogeneities [m] (<= 0: uniform), as pumas_locals_cb does. */
+typedef double pumas_b200_locals_fn(const void * user_data, int medium,
+    const struct pumas_state * state, double * density, double * magnet);
+
+struct pumas_b200_callbacks {
+        pumas_b200_medium_fn * medium; /* device function */
+        pumas_b200_locals_fn * locals; /* device function, or NULL */
+        const void * user_data;        /* device pointer handed back */
+        int n_media;
+        int material[PUMAS_B200_MAX_LAYERS];   /* physics material of medium i */
+        int has_locals[PUMAS_B200_MAX_LAYERS]; /* 0: pumas_medium::locals == NULL
+                                                * (pumas.c:5533) */
+};
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,10 @@ both sides load the same bytes. Outputs (gzip, committed):
                                            KKP / KKP / BBKS
     tests/golden/rock.muon.abm.pumas.gz    oracle/data/rock.xml, muon, models
                                            ABB / SSR / BM
+    tests/golden/rock.muon.usr.pumas.gz    oracle/data/rock.xml, muon, the user
+                                           registered bremsstrahlung model of
+                                           examples/user_dcs.h (BHS) / SSR /
+                                           DRSS
 """
 import ctypes
 import gzip
@@ -30,7 +34,9 @@ JOBS = [
     (1, "ice/ice.xml", "ice.tau.pumas", None),
     (0, "rock/rock.xml", "rock.muon.kkb.pumas", (b"KKP", b"KKP", b"BBKS")),
     (0, "rock/rock.xml", "rock.muon.abm.pumas", (b"ABB", b"SSR", b"BM")),
+    (0, "rock/rock.xml", "rock.muon.usr.pumas", (b"BHS", b"SSR", b"DRSS")),
 ]
+assert lib.oracle_register_user_dcs() == 0
 if len(sys.argv) > 1:
     JOBS = [j for j in JOBS if j[2] in sys.argv[1:]]
 

@@ -114,8 +114,84 @@ static enum pumas_step oracle_medium_cb(struct pumas_context * context,
         return (enum pumas_step)g->step_type;
 }
 
+static void oracle_silent_handler(
+    enum pumas_return rc, pumas_function_t * caller, const char * message);
+
+/* ---- user media (examples/user_media.h) through host callbacks -----------
+ * The same source the device build of examples/user_media.cu compiles, here as
+ * pumas_medium_cb / pumas_locals_cb of the reference (tests/test_user_media.py). */
+#include "../examples/user_media.h"
+
+static struct user_media oracle_user_media;
+static int oracle_user_media_on = 0;
+
+static double oracle_user_locals(struct pumas_medium * medium,
+    struct pumas_state * state, struct pumas_locals * locals)
+{
+        const struct oracle_medium * m = (struct oracle_medium *)medium;
+        locals->magnet[0] = locals->magnet[1] = locals->magnet[2] = 0.;
+        return user_media_density(
+            &oracle_user_media, m->layer, state->position, &locals->density);
+}
+
+static enum pumas_step oracle_user_medium_cb(struct pumas_context * context,
+    struct pumas_state * state, struct pumas_medium ** medium_ptr,
+    double * step_ptr)
+{
+        int medium = -1;
+        const int backward =
+            (context->mode.direction == PUMAS_MODE_FORWARD) ? 0 : 1;
+        const int type = user_media_locate(&oracle_user_media, state->position,
+            state->direction, backward, (medium_ptr != NULL) ? &medium : NULL,
+            step_ptr);
+        if (medium_ptr != NULL)
+                *medium_ptr = (medium < 0) ? NULL : &oracle_media[medium].api;
+        return (enum pumas_step)type;
+}
+
+/* Switch the next oracle_transport_n calls to the user media (`shells` != NULL;
+ * materials[i]: material of shell i) or back to the descriptor (NULL). */
+void oracle_set_user_media(const struct user_media * shells, const int * materials)
+{
+        if (shells == NULL) {
+                oracle_user_media_on = 0;
+                return;
+        }
+        memcpy(&oracle_user_media, shells, sizeof oracle_user_media);
+        int i;
+        for (i = 0; i < shells->n_shells; i++) {
+                oracle_media[i].api.material = materials[i];
+                oracle_media[i].api.locals = &oracle_user_locals;
+                oracle_media[i].layer = i;
+        }
+        oracle_user_media_on = 1;
+}
+
+/* ---- user DCS model (examples/user_dcs.h), registered with the reference -- */
+#include "../examples/user_dcs.h"
+
+static double oracle_user_dcs(double Z, double A, double m, double K, double q)
+{
+        return user_dcs_bremsstrahlung(Z, A, m, K, q);
+}
+
+/* pumas_dcs_register (pumas.c:15422) of the model; idempotent. */
+int oracle_register_user_dcs(void)
+{
+        static int done = 0;
+        if (done) return PUMAS_RETURN_SUCCESS;
+        pumas_handler_cb * previous = pumas_error_handler_get();
+        pumas_error_handler_set(&oracle_silent_handler);
+        const int rc = pumas_dcs_register(
+            PUMAS_PROCESS_BREMSSTRAHLUNG, USER_DCS_MODEL, &oracle_user_dcs);
+        pumas_error_handler_set(previous);
+        if (rc == PUMAS_RETURN_SUCCESS) done = 1;
+        return rc;
+}
+
 static void oracle_set_geometry(const struct pumas_b200_geometry * geometry)
 {
+        if (oracle_user_media_on) return;
         memcpy(&oracle_geometry, geometry, sizeof oracle_geometry);
         int i;
         for (i = 0; i < PUMAS_B200_MAX_LAYERS; i++) {
@@ -161,7 +237,8 @@ static void * oracle_worker(void * arg)
         context->event = job->settings->event;
         context->limit = job->settings->limit;
         context->accuracy = job->settings->accuracy;
-        context->medium = &oracle_medium_cb;
+        context->medium =
+            oracle_user_media_on ? &oracle_user_medium_cb : &oracle_medium_cb;
         context->random = &oracle_random;
         struct oracle_user_data * u = context->user_data;
         struct simulation_context * hidden =

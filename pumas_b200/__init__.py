@@ -85,6 +85,15 @@ class Geometry(ctypes.Structure):
                 ("layer", Layer * MAX_LAYERS)]
 
 
+class Callbacks(ctypes.Structure):
+    """struct pumas_b200_callbacks (include/pumas_b200_geometry.h): device
+    function pointers, filled by the library that holds the functions."""
+    _fields_ = [("medium", ctypes.c_void_p), ("locals", ctypes.c_void_p),
+                ("user_data", ctypes.c_void_p), ("n_media", ctypes.c_int),
+                ("material", ctypes.c_int * MAX_LAYERS),
+                ("has_locals", ctypes.c_int * MAX_LAYERS)]
+
+
 def uniform_geometry(material, density=None):
     """One infinite medium (examples/pumas/straight.c:61-74)."""
     g = Geometry()
@@ -126,6 +135,14 @@ def layered_geometry(z, layers, step_type=STEP_RAW):
             for k, b in enumerate(l.get("magnet", (0., 0., 0.))):
                 g.layer[i].magnet[k] = b
     return g
+
+
+def planar_callbacks(geometry):
+    """The planar media of `geometry` behind the callback interface."""
+    cb = Callbacks()
+    _check(library().pumas_b200_planar_callbacks(
+        ctypes.byref(geometry), ctypes.byref(cb)))
+    return cb
 
 
 def make_states(n, energy, charge=-1., direction=(0., 0., 1.), weight=1.,
@@ -189,6 +206,12 @@ def library():
         ctypes.POINTER(ContextStruct), ctypes.POINTER(ctypes.c_ulong)]
     lib.pumas_b200_context_geometry_set.argtypes = [
         ctypes.POINTER(ContextStruct), ctypes.POINTER(Geometry)]
+    lib.pumas_b200_context_callbacks_set.argtypes = [
+        ctypes.POINTER(ContextStruct), ctypes.POINTER(Callbacks)]
+    lib.pumas_b200_planar_callbacks.argtypes = [
+        ctypes.POINTER(Geometry), ctypes.POINTER(Callbacks)]
+    lib.pumas_b200_planar_callbacks_free.argtypes = [ctypes.POINTER(Callbacks)]
+    lib.pumas_b200_planar_callbacks_free.restype = None
     lib.pumas_b200_context_track_offset_set.argtypes = [
         ctypes.POINTER(ContextStruct), ctypes.c_ulonglong]
     lib.pumas_b200_context_stream_set.argtypes = [
@@ -422,6 +445,12 @@ class Context:
     def geometry(self, geometry):
         _check(library().pumas_b200_context_geometry_set(
             self._ptr, ctypes.byref(geometry)))
+
+    def callbacks(self, callbacks):
+        """`__device__` medium / locals functions (a Callbacks table, or None
+        to go back to the descriptor)."""
+        _check(library().pumas_b200_context_callbacks_set(
+            self._ptr, None if callbacks is None else ctypes.byref(callbacks)))
 
     def track_offset(self, offset):
         _check(library().pumas_b200_context_track_offset_set(self._ptr, offset))

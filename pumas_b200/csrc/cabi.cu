@@ -45,6 +45,31 @@ struct pumas_physics {
 
 namespace {
 
+/* ---- user registered DCS models (dcs_stack, pumas.c:15373-15460) -----------
+ * A model is a name and a host function, as in the reference, plus -- for the
+ * transport kernels -- its `__device__` counterpart
+ * (pumas_b200_dcs_register_device). 64 entries in all, 8 of them built in. */
+struct UserModel {
+        int process;
+        std::string name;
+        pumas_dcs_t * host;
+        pumas_dcs_t * device; /* a device function pointer, or NULL */
+};
+constexpr size_t USER_MODEL_STACK = 64 - 8;
+const char * const PROCESS_NAME[3] = { "bremsstrahlung", "pair production",
+        "photonuclear" };
+std::vector<UserModel> g_user_models;
+std::mutex g_user_models_mutex;
+
+const UserModel * user_model_find(int process, const char * name)
+{
+        for (size_t i = 0; i < g_user_models.size(); i++)
+                if ((g_user_models[i].process == process) &&
+                    (g_user_models[i].name == name))
+                        return &g_user_models[i];
+        return nullptr;
+}
+
 /* struct simulation_context (pumas.c:426-477): the public struct comes first
  * so that `struct pumas_context *` is a pointer to this object. */
 struct ContextImpl {
@@ -55,6 +80,14 @@ struct ContextImpl {
         unsigned long long track_offset;
         int has_geometry;
         struct pumas_b200_geometry geometry;
+        /* `__device__` medium / locals callbacks (kernels_callback.cu); take
+         * precedence over the descriptor */
+        int has_callbacks;
+        struct pumas_b200_callbacks callbacks;
+        /* the descriptor behind the callback interface, for a physics with
+         * user DCS models (those run on the device-linked kernel only) */
+        int has_planar;
+        struct pumas_b200_callbacks planar;
         cudaStream_t stream;
         /* device staging buffers (grown on demand) */
         long capacity;
@@ -384,6 +417,8 @@ const char * pumas_error_function(pumas_function_t * caller)
         NAME(pumas_b200_context_transport_async)
         NAME(pumas_b200_context_synchronize)
         NAME(pumas_b200_context_geometry_set)
+        NAME(pumas_b200_context_callbacks_set)
+        NAME(pumas_b200_planar_callbacks)
         NAME(pumas_b200_context_track_offset_set)
         NAME(pumas_b200_context_stream_set)
         NAME(pumas_b200_context_kernel_set)
@@ -394,6 +429,7 @@ const char * pumas_error_function(pumas_function_t * caller)
         NAME(pumas_physics_dcs)
         NAME(pumas_dcs_get)
         NAME(pumas_dcs_register)
+        NAME(pumas_b200_dcs_register_device)
         NAME(pumas_dcs_range)
 #undef NAME
         return nullptr;
@@ -475,6 +511,24 @@ enum pumas_return pumas_physics_load(
                 physics_delete(physics);
                 return RAISE(pumas_physics_load, (enum pumas_return)rc, "%s",
                     err.c_str());
+        }
+        /* models the dump names that are not built in: the user's, which must
+         * be registered by now (dcs_get, pumas.c:10954; the reference fails
+         * the same way) */
+        for (int i = 0; i < 3; i++) {
+                if (physics->host.view.model[i] != pb::MODEL_USER) continue;
+                std::lock_guard<std::mutex> lock(g_user_models_mutex);
+                const UserModel * m =
+                    user_model_find(i, physics->host.model[i].c_str());
+                if (m == nullptr) {
+                        const std::string name = physics->host.model[i];
+                        physics_delete(physics);
+                        return RAISE(pumas_physics_load,
+                            PUMAS_RETURN_MODEL_ERROR,
+                            "cannot find %s model for %s process",
+                            name.c_str(), PROCESS_NAME[i]);
+                }
+                physics->host.view.user_dcs[i] = m->host;
         }
         if (physics->host.view.max_components > pb::MAX_COMPONENTS) {
                 physics_delete(physics);
@@ -1015,6 +1069,7 @@ void pumas_context_destroy(struct pumas_context ** context)
         if ((context == nullptr) || (*context == nullptr)) return;
         ContextImpl * c = reinterpret_cast<ContextImpl *>(*context);
         context_free_buffers(c);
+        if (c->has_planar) cudaFree(const_cast<void *>(c->planar.user_data));
         if (c->d_status) cudaFree(c->d_status);
         if (c->d_workspace) cudaFree(c->d_workspace);
         if (c->events_ready) {
@@ -1118,7 +1173,84 @@ enum pumas_return pumas_b200_context_geometry_set(
         }
         c->geometry = *geometry;
         c->has_geometry = 1;
+        if (c->has_planar) {
+                cudaFree(const_cast<void *>(c->planar.user_data));
+                c->has_planar = 0;
+        }
         return PUMAS_RETURN_SUCCESS;
+}
+
+/* Device callbacks (pumas.h:509-511, 348-349 on the device): see
+ * pumas_b200_geometry.h and kernels_callback.cu. NULL: back to the descriptor. */
+enum pumas_return pumas_b200_context_callbacks_set(struct pumas_context * context,
+    const struct pumas_b200_callbacks * callbacks)
+{
+        if (context == nullptr)
+                return RAISE(pumas_b200_context_callbacks_set,
+                    PUMAS_RETURN_VALUE_ERROR, "a NULL pointer was provided");
+        ContextImpl * c = reinterpret_cast<ContextImpl *>(context);
+        if (callbacks == nullptr) {
+                c->has_callbacks = 0;
+                return PUMAS_RETURN_SUCCESS;
+        }
+        const pb::Physics & p = c->physics->host.view;
+        if (callbacks->medium == nullptr)
+                return RAISE(pumas_b200_context_callbacks_set,
+                    PUMAS_RETURN_MEDIUM_ERROR, "no medium function");
+        if ((callbacks->n_media < 1) ||
+            (callbacks->n_media > PUMAS_B200_MAX_LAYERS))
+                return RAISE(pumas_b200_context_callbacks_set,
+                    PUMAS_RETURN_MEDIUM_ERROR, "invalid number of media [%d]",
+                    callbacks->n_media);
+        for (int i = 0; i < callbacks->n_media; i++) {
+                const int m = callbacks->material[i];
+                if ((m < 0) || (m >= p.n_materials))
+                        return RAISE(pumas_b200_context_callbacks_set,
+                            PUMAS_RETURN_INDEX_ERROR,
+                            "invalid material index [%d]", m);
+                if (callbacks->has_locals[i] && (callbacks->locals == nullptr))
+                        return RAISE(pumas_b200_context_callbacks_set,
+                            PUMAS_RETURN_MEDIUM_ERROR,
+                            "medium %d has locals but there is no locals "
+                            "function", i);
+        }
+        c->callbacks = *callbacks;
+        c->has_callbacks = 1;
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* The library's own client of the callback interface: the planar media of a
+ * descriptor as device functions, user_data = a device copy of `geometry`. */
+enum pumas_return pumas_b200_planar_callbacks(
+    const struct pumas_b200_geometry * geometry,
+    struct pumas_b200_callbacks * callbacks)
+{
+        if ((geometry == nullptr) || (callbacks == nullptr))
+                return RAISE(pumas_b200_planar_callbacks,
+                    PUMAS_RETURN_VALUE_ERROR, "a NULL pointer was provided");
+        if (((geometry->kind != PUMAS_B200_GEOMETRY_UNIFORM) &&
+                (geometry->kind != PUMAS_B200_GEOMETRY_LAYERS)) ||
+            (geometry->n_layers < 1) ||
+            (geometry->n_layers > PUMAS_B200_MAX_LAYERS))
+                return RAISE(pumas_b200_planar_callbacks,
+                    PUMAS_RETURN_MEDIUM_ERROR, "invalid geometry");
+        std::string why;
+        if (!device_usable(&why))
+                return RAISE(pumas_b200_planar_callbacks,
+                    PUMAS_RETURN_INTERNAL_ERROR, "%s", why.c_str());
+        const cudaError_t e = pb::planar_callbacks(*geometry, callbacks);
+        if (e != cudaSuccess)
+                return RAISE(pumas_b200_planar_callbacks,
+                    PUMAS_RETURN_INTERNAL_ERROR, "CUDA error (%s)",
+                    cudaGetErrorString(e));
+        return PUMAS_RETURN_SUCCESS;
+}
+
+void pumas_b200_planar_callbacks_free(struct pumas_b200_callbacks * callbacks)
+{
+        if ((callbacks == nullptr) || (callbacks->user_data == nullptr)) return;
+        cudaFree(const_cast<void *>(callbacks->user_data));
+        callbacks->user_data = nullptr;
 }
 
 /* pumas.c:2415-2492. The state of the random streams of a context is its seed
@@ -1452,19 +1584,24 @@ enum pumas_return transport_batch(pumas_function_t * caller,
         if (physics == nullptr)
                 return RAISE_C(PUMAS_RETURN_PHYSICS_ERROR,
                     "the Physics has not been initialised");
-        if (!c->has_geometry) {
+        if (!c->has_geometry && !c->has_callbacks) {
                 /* a host `pumas_medium_cb` cannot run inside a kernel: say so
                  * instead of ignoring it */
                 if (context->medium != nullptr)
                         return RAISE_C(PUMAS_RETURN_MEDIUM_ERROR,
                             "context->medium is a host callback: it cannot "
                             "run on the device. Describe the geometry with "
-                            "pumas_b200_context_geometry_set");
+                            "pumas_b200_context_geometry_set or give device "
+                            "functions to pumas_b200_context_callbacks_set");
                 return RAISE_C(PUMAS_RETURN_MEDIUM_ERROR, "no medium specified");
         }
         if ((context->recorder != nullptr) && async)
                 return RAISE_C(PUMAS_RETURN_VALUE_ERROR,
                     "a recorder needs the synchronous entry points");
+        if ((context->recorder != nullptr) && c->has_callbacks)
+                return RAISE_C(PUMAS_RETURN_VALUE_ERROR,
+                    "the recorder runs on the built-in media only (set the "
+                    "geometry with pumas_b200_context_geometry_set)");
 
         /* Configuration checks, pumas.c:3152-3177. */
         const pb::Settings cfg = settings_from(context);
@@ -1512,6 +1649,25 @@ enum pumas_return transport_batch(pumas_function_t * caller,
         pb::Physics d_view;
         enum pumas_return rc = physics_upload(caller, physics, &d_view);
         if (rc != PUMAS_RETURN_SUCCESS) return rc;
+        /* user DCS models (pumas_dcs_register): the device functions, called
+         * by the device-linked kernel (kernels_callback.cu) only */
+        bool user_models = false;
+        for (int i = 0; i < 3; i++) {
+                if (hp.model[i] != pb::MODEL_USER) continue;
+                std::lock_guard<std::mutex> lock(g_user_models_mutex);
+                const UserModel * m =
+                    user_model_find(i, physics->host.model[i].c_str());
+                if ((m == nullptr) || (m->device == nullptr))
+                        return RAISE_C(PUMAS_RETURN_MODEL_ERROR,
+                            "the %s model of the %s process has no device "
+                            "function (pumas_b200_dcs_register_device)",
+                            physics->host.model[i].c_str(), PROCESS_NAME[i]);
+                d_view.user_dcs[i] = m->device;
+                user_models = true;
+        }
+        if (user_models && (context->recorder != nullptr))
+                return RAISE_C(PUMAS_RETURN_MODEL_ERROR,
+                    "the recorder kernel does not call user DCS models");
 
         if (!c->seed_set) {
                 rc = pumas_context_random_seed_set(context, nullptr);
@@ -1585,7 +1741,20 @@ enum pumas_return transport_batch(pumas_function_t * caller,
         if ((e == cudaSuccess) && !c->pending)
                 e = cudaMemsetAsync(c->d_status, 0, sizeof(int), stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->ev0, stream);
-        if (e == cudaSuccess)
+        if ((e == cudaSuccess) && user_models && !c->has_callbacks) {
+                /* the built-in media behind the callback interface */
+                if (!c->has_planar) {
+                        e = pb::planar_callbacks(c->geometry, &c->planar);
+                        if (e == cudaSuccess) c->has_planar = 1;
+                }
+        }
+        if ((e == cudaSuccess) && (c->has_callbacks || user_models))
+                e = pb::launch_transport_callbacks(d_view, cfg,
+                    c->has_callbacks ? c->callbacks : c->planar,
+                    (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_states,
+                    d_events, d_media, c->d_status, c->d_random, c->d_steps,
+                    c->d_workspace, stream);
+        else if (e == cudaSuccess)
                 e = pb::launch_transport(d_view, physics->host.view, cfg,
                     c->geometry,
                     (uint64_t)c->seed, (uint64_t)c->track_offset, n, d_states,
@@ -1798,9 +1967,6 @@ const ModelEntry MODELS[3][3] = {
             { "BM", &api_dcs_photonuclear_BM },
             { "BBKS", &api_dcs_photonuclear_BBKS } }
 };
-const char * const PROCESS_NAME[3] = { "bremsstrahlung", "pair production",
-        "photonuclear" };
-
 } /* namespace */
 
 extern "C" {
@@ -1815,6 +1981,13 @@ enum pumas_return pumas_physics_dcs(const struct pumas_physics * physics,
                 return RAISE(pumas_physics_dcs, PUMAS_RETURN_INDEX_ERROR,
                     "bad process (expected a value in [0, 2], got %u)",
                     (unsigned int)process);
+        if (physics->host.view.model[process] == pb::MODEL_USER) {
+                if (dcs != nullptr)
+                        *dcs = physics->host.view.user_dcs[process];
+                if (model != nullptr)
+                        *model = physics->host.model[process].c_str();
+                return PUMAS_RETURN_SUCCESS;
+        }
         const ModelEntry & entry =
             MODELS[process][physics->host.view.model[process]];
         if (dcs != nullptr) *dcs = entry.dcs;
@@ -1838,19 +2011,84 @@ enum pumas_return pumas_dcs_get(
                         return PUMAS_RETURN_SUCCESS;
                 }
         }
+        {
+                std::lock_guard<std::mutex> lock(g_user_models_mutex);
+                const UserModel * m = user_model_find((int)process, model);
+                if (m != nullptr) {
+                        *dcs = m->host;
+                        return PUMAS_RETURN_SUCCESS;
+                }
+        }
         *dcs = nullptr;
         return RAISE(pumas_dcs_get, PUMAS_RETURN_MODEL_ERROR,
             "model %s not found for %s process", model, PROCESS_NAME[process]);
 }
 
+/* pumas.c:15422-15460. The host function serves the host side API
+ * (pumas_dcs_get, pumas_physics_dcs) as in the reference; the transport
+ * kernels need its `__device__` counterpart as well, given by
+ * pumas_b200_dcs_register_device. */
 enum pumas_return pumas_dcs_register(
     enum pumas_process process, const char * model, pumas_dcs_t * dcs)
 {
-        (void)process;
-        (void)dcs;
-        return RAISE(pumas_dcs_register, PUMAS_RETURN_MODEL_ERROR,
-            "cannot register model %s: a host function cannot be evaluated "
-            "by the transport kernels", (model != nullptr) ? model : "(null)");
+        if (((int)process < 0) || (process > PUMAS_PROCESS_PHOTONUCLEAR))
+                return RAISE(pumas_dcs_register, PUMAS_RETURN_INDEX_ERROR,
+                    "bad process (expected an index in [0, %d], got %u)",
+                    (int)PUMAS_PROCESS_PHOTONUCLEAR, (unsigned int)process);
+        if (dcs == nullptr)
+                return RAISE(pumas_dcs_register, PUMAS_RETURN_VALUE_ERROR,
+                    "bad dcs (expected a function, got nil)");
+        if (model == nullptr)
+                return RAISE(pumas_dcs_register, PUMAS_RETURN_VALUE_ERROR,
+                    "bad model (expected a string, got nil)");
+        bool known = false;
+        for (int k = 0; k < 3; k++) {
+                const ModelEntry & entry = MODELS[process][k];
+                if ((entry.name != nullptr) && (strcmp(entry.name, model) == 0))
+                        known = true;
+        }
+        std::lock_guard<std::mutex> lock(g_user_models_mutex);
+        if (known || (user_model_find((int)process, model) != nullptr))
+                return RAISE(pumas_dcs_register, PUMAS_RETURN_MODEL_ERROR,
+                    "model %s already registered for %s process", model,
+                    PROCESS_NAME[process]);
+        if (g_user_models.size() >= USER_MODEL_STACK)
+                return RAISE(pumas_dcs_register, PUMAS_RETURN_MEMORY_ERROR,
+                    "max stack size reached");
+        UserModel m;
+        m.process = (int)process;
+        m.name = model;
+        m.host = dcs;
+        m.device = nullptr;
+        g_user_models.push_back(m);
+        return PUMAS_RETURN_SUCCESS;
+}
+
+/* New. The `__device__` function of a model registered with
+ * pumas_dcs_register: a device function pointer of the device link unit of the
+ * kernels (`python -m pumas_b200.build --user`). */
+enum pumas_return pumas_b200_dcs_register_device(
+    enum pumas_process process, const char * model, pumas_dcs_t * device_dcs)
+{
+        if (((int)process < 0) || (process > PUMAS_PROCESS_PHOTONUCLEAR))
+                return RAISE(pumas_b200_dcs_register_device,
+                    PUMAS_RETURN_INDEX_ERROR,
+                    "bad process (expected an index in [0, %d], got %u)",
+                    (int)PUMAS_PROCESS_PHOTONUCLEAR, (unsigned int)process);
+        if ((device_dcs == nullptr) || (model == nullptr))
+                return RAISE(pumas_b200_dcs_register_device,
+                    PUMAS_RETURN_VALUE_ERROR, "a NULL pointer was provided");
+        std::lock_guard<std::mutex> lock(g_user_models_mutex);
+        for (size_t i = 0; i < g_user_models.size(); i++) {
+                UserModel & m = g_user_models[i];
+                if ((m.process == (int)process) && (m.name == model)) {
+                        m.device = device_dcs;
+                        return PUMAS_RETURN_SUCCESS;
+                }
+        }
+        return RAISE(pumas_b200_dcs_register_device, PUMAS_RETURN_MODEL_ERROR,
+            "cannot find %s model for %s process (register the host function "
+            "with pumas_dcs_register first)", model, PROCESS_NAME[process]);
 }
 
 const char * pumas_dcs_default(enum pumas_process process)

@@ -67,6 +67,18 @@ cudaError_t launch_transport(const Physics & p, const Physics & host_view,
     unsigned int * n_random, unsigned int * n_steps, void * workspace,
     int kernel, cudaStream_t stream);
 
+/* The same over `__device__` medium / locals callbacks (kernels_callback.cu):
+ * the general resident kernel instantiated on CallbackGeometry. */
+cudaError_t launch_transport_callbacks(const Physics & p, const Settings & cfg,
+    const struct pumas_b200_callbacks & callbacks, uint64_t seed,
+    uint64_t offset, long n, State * states, int * events, int * media,
+    int * status, unsigned int * n_random, unsigned int * n_steps,
+    void * workspace, cudaStream_t stream);
+/* The planar media of `geo` as callbacks (user_data: a device copy of `geo`,
+ * to be released with cudaFree). */
+cudaError_t planar_callbacks(
+    const Geometry & geo, struct pumas_b200_callbacks * cb);
+
 } /* namespace pb */
 
 #endif

@@ -759,20 +759,34 @@ PB_FN double dcs_photonuclear_d2(const Physics & p, const Element & el,
 }
 
 /* ---- process dispatch (dcs_get, pumas.c:10954; wrappers 11003-11048) ----- */
+/* Is the user's model of the process callable here? On the host always (the
+ * host view holds host functions); on the device in the kernels device-linked
+ * with user code only. */
+#if !defined(__CUDA_ARCH__) || defined(PB_USER_DCS)
+#define PB_USER_DCS_CALL(p, i, el, K, q)                                       \
+        (((p).model[i] == MODEL_USER) && ((p).user_dcs[i] != nullptr))
+#else
+#define PB_USER_DCS_CALL(p, i, el, K, q) false
+#endif
+
 PB_FN double dcs_model(
     const Physics & p, int process, const Element & el, double K, double q)
 {
         if (process == 3) return dcs_ionisation(p, el, K, q);
         double d;
         if (process == 0) {
-                if (p.model[0] == BREMSSTRAHLUNG_KKP)
+                if (PB_USER_DCS_CALL(p, 0, el, K, q))
+                        d = p.user_dcs[0](el.Z, el.A, p.mass, K, q);
+                else if (p.model[0] == BREMSSTRAHLUNG_KKP)
                         d = dcs_bremsstrahlung_KKP(el, p.mass, K, q);
                 else if (p.model[0] == BREMSSTRAHLUNG_ABB)
                         d = dcs_bremsstrahlung_ABB(el, p.mass, K, q);
                 else
                         d = dcs_bremsstrahlung_SSR(p, el, p.mass, K, q);
         } else if (process == 1) {
-                if (p.model[1] == PAIR_PRODUCTION_KKP)
+                if (PB_USER_DCS_CALL(p, 1, el, K, q))
+                        d = p.user_dcs[1](el.Z, el.A, p.mass, K, q);
+                else if (p.model[1] == PAIR_PRODUCTION_KKP)
                         d = dcs_pair_production_KKP(el, p.mass, K, q);
                 else
                         d = dcs_pair_production_SSR(p, el, p.mass, K, q);
@@ -780,7 +794,9 @@ PB_FN double dcs_model(
                 double qmin, qmax;
                 dcs_photonuclear_range(p.mass, K, &qmin, &qmax);
                 if ((q < qmin) || (q > qmax)) return 0.;
-                if (p.model[2] == PHOTONUCLEAR_BM)
+                if (PB_USER_DCS_CALL(p, 2, el, K, q))
+                        d = p.user_dcs[2](el.Z, el.A, p.mass, K, q);
+                else if (p.model[2] == PHOTONUCLEAR_BM)
                         d = dcs_photonuclear_BM(el, p.mass, K, q);
                 else if (p.model[2] == PHOTONUCLEAR_BBKS)
                         d = dcs_photonuclear_BBKS(el, p.mass, K, q);

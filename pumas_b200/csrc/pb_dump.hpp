@@ -263,8 +263,7 @@ inline int load_physics_bytes(
         }
 
         /* Model names -> indices (pb_dcs_models.h; dcs_stack,
-         * pumas.c:15381-15390). User registered models have no device
-         * implementation. */
+         * pumas.c:15381-15390). */
         const uint64_t model_ptr[3] = { h.model_bremsstrahlung,
                 h.model_pair_production, h.model_photonuclear };
         const char * known[3][3] = { { "SSR", "KKP", "ABB" },
@@ -281,12 +280,9 @@ inline int load_physics_bytes(
                         if ((known[i][k] != nullptr) &&
                             (hp.model[i] == known[i][k]))
                                 hp.model_index[i] = k;
-                if (hp.model_index[i] < 0) {
-                        err = "unsupported DCS model `" + hp.model[i] +
-                            "' (user registered models have no device "
-                            "implementation)";
-                        return 14; /* PUMAS_RETURN_MODEL_ERROR */
-                }
+                /* (anything else: a user registered model, resolved by the
+                 * caller against its registry; pumas.c:15422) */
+                if (hp.model_index[i] < 0) hp.model_index[i] = MODEL_USER;
         }
 
         /* Elements. */
@@ -482,7 +478,10 @@ inline int load_physics_bytes(
         v.max_components = h.max_components;
         v.n_table_dcs = h.n_table_dcs;
         v.particle = h.particle;
-        for (int i = 0; i < 3; i++) v.model[i] = hp.model_index[i];
+        for (int i = 0; i < 3; i++) {
+                v.model[i] = hp.model_index[i];
+                v.user_dcs[i] = nullptr;
+        }
         v.pad_ = 0;
         v.ctau = h.ctau;
         v.mass = h.mass;

@@ -62,6 +62,26 @@ PB_FN int medium_locate(const Geometry & g, int direction, const State & state,
         return g.step_type;
 }
 
+/* The locals callback of a layer (examples/pumas/geometry.c:64-97): density,
+ * field, and the size of the inhomogeneities (0: uniform). */
+PB_FN double layer_locals(const struct pumas_b200_layer & l, const State & state,
+    double * density, double * magnet)
+{
+        double step_max;
+        magnet[0] = l.magnet[0];
+        magnet[1] = l.magnet[1];
+        magnet[2] = l.magnet[2];
+        if (l.density_model == PUMAS_B200_DENSITY_EXPONENTIAL) {
+                *density = l.density * xexp(-state.position[2] / l.scale);
+                const double uz = fabs(state.direction[2]);
+                step_max = l.scale / ((uz <= l.eps) ? l.eps : uz);
+        } else {
+                *density = l.density;
+                step_max = 0.;
+        }
+        return step_max;
+}
+
 /* transport_set_locals, pumas.c:5528-5552. Returns the proposed locals step
  * times the accuracy (<= 0: uniform). */
 PB_FN double set_locals(const Physics & p, const Geometry & g, double accuracy,
@@ -74,18 +94,8 @@ PB_FN double set_locals(const Physics & p, const Geometry & g, double accuracy,
                 locals->magnetized = 0;
                 return 0;
         }
-        double step_max;
-        locals->magnet[0] = l.magnet[0];
-        locals->magnet[1] = l.magnet[1];
-        locals->magnet[2] = l.magnet[2];
-        if (l.density_model == PUMAS_B200_DENSITY_EXPONENTIAL) {
-                locals->density = l.density * xexp(-state.position[2] / l.scale);
-                const double uz = fabs(state.direction[2]);
-                step_max = l.scale / ((uz <= l.eps) ? l.eps : uz);
-        } else {
-                locals->density = l.density;
-                step_max = 0.;
-        }
+        const double step_max =
+            layer_locals(l, state, &locals->density, locals->magnet);
         if (locals->density <= 0)
                 locals->density = p.material_density[l.material];
         const double * b = locals->magnet;
@@ -136,6 +146,52 @@ PB_FN double set_locals(const Physics & p, const UniformGeometry & g, double,
         locals->magnet[0] = locals->magnet[1] = locals->magnet[2] = 0.;
         locals->magnetized = 0;
         return 0;
+}
+
+/* ---- callbacks -------------------------------------------------------------
+ * The geometry behind two function pointers (device functions on the GPU,
+ * host functions in the CPU build): pumas_medium_cb / pumas_locals_cb. */
+struct CallbackGeometry {
+        struct pumas_b200_callbacks cb;
+};
+
+PB_FN int geo_material(const CallbackGeometry & g, int medium)
+{
+        return g.cb.material[medium];
+}
+PB_FN bool geo_has_boundaries(const CallbackGeometry &) { return true; }
+PB_FN bool geo_has_locals(const CallbackGeometry &) { return true; }
+
+PB_FN int medium_locate(const CallbackGeometry & g, int direction,
+    const State & state, bool want_medium, int * medium, bool want_step,
+    double * step_ptr)
+{
+        return g.cb.medium(g.cb.user_data,
+            reinterpret_cast<const struct pumas_state *>(&state),
+            (direction == MODE_BACKWARD) ? 1 : 0, want_medium ? medium : nullptr,
+            want_step ? step_ptr : nullptr);
+}
+
+/* transport_set_locals, pumas.c:5528-5552 */
+PB_FN double set_locals(const Physics & p, const CallbackGeometry & g,
+    double accuracy, int medium, const State & state, Locals * locals)
+{
+        const int material = g.cb.material[medium];
+        if (!g.cb.has_locals[medium] || (g.cb.locals == nullptr)) {
+                locals->density = p.material_density[material];
+                locals->magnet[0] = locals->magnet[1] = locals->magnet[2] = 0.;
+                locals->magnetized = 0;
+                return 0;
+        }
+        const double step_max = g.cb.locals(g.cb.user_data, medium,
+            reinterpret_cast<const struct pumas_state *>(&state),
+            &locals->density, locals->magnet);
+        if (locals->density <= 0)
+                locals->density = p.material_density[material];
+        const double * b = locals->magnet;
+        locals->magnetized =
+            ((b[0] != 0.) || (b[1] != 0.) || (b[2] != 0.)) ? 1 : 0;
+        return step_max * accuracy;
 }
 
 } /* namespace pb */

@@ -37,6 +37,10 @@ struct Element {
         double wood_saxon;        /* dcs_wood_saxon(Z, A) pumas.c:14732-14748 */
 };
 
+/* Index of a user registered DCS model in Physics::model (the built-in ones
+ * are 0 .. 2, pb_dcs_models.h). */
+constexpr int MODEL_USER = 3;
+
 struct Physics {
         int n_energies;
         int n_materials;
@@ -50,6 +54,12 @@ struct Physics {
          * bremsstrahlung, [1] pair production, [2] photonuclear */
         int model[3];
         int pad_;
+        /* model[i] == MODEL_USER: a model registered by the user
+         * (pumas_dcs_register, pumas.c:15422), as a function of the side the
+         * view belongs to: a host function in the host view, a `__device__`
+         * function (pumas_b200_dcs_register_device) in a device view. Only
+         * kernels compiled with PB_USER_DCS (kernels_callback.cu) call it. */
+        double (*user_dcs[3])(double Z, double A, double m, double K, double q);
         double ctau;
         double mass;
         double cutoff;

@@ -1093,9 +1093,9 @@ struct Loop {
  * keeping 20 registers per track for them (-23 % register spills, +5 %
  * tracks/s). Values are the ones the track already holds (set_locals,
  * medium_locate and straight_flag above give nothing else). */
-template <class Cfg>
+template <class Cfg, class Geo>
 PB_FN void loop_canonical(
-    const Physics &, const Cfg & cfg, const Geometry &, Track & trk, Loop &)
+    const Physics &, const Cfg & cfg, const Geo &, Track & trk, Loop &)
 {
         /* (the lifetime is only drawn, and read, for randomised decays) */
         if (cfg.decay != MODE_RANDOMISED) trk.lifetime = 0.;

@@ -165,5 +165,10 @@ def test_errors():
     assert ours.pumas_dcs_range(-1, 1., 1., 1., a, a) == 7
     ours.pumas_dcs_register.argtypes = [ctypes.c_int, ctypes.c_char_p,
                                         ctypes.c_void_p]
-    assert ours.pumas_dcs_register(0, b"mine", None) == 14
+    # pumas.c:15422-15460: nil function, nil name, bad process, known name
+    assert ours.pumas_dcs_register(0, b"mine", None) == 24  # VALUE_ERROR
+    fn = ctypes.c_void_p(1)
+    assert ours.pumas_dcs_register(0, None, fn) == 24
+    assert ours.pumas_dcs_register(3, b"mine", fn) == 7
+    assert ours.pumas_dcs_register(0, b"SSR", fn) == 14  # MODEL_ERROR
     assert ours.pumas_physics_dcs(None, 0, None, None) == 8  # PHYSICS_ERROR
