@@ -615,6 +615,12 @@ PUMAS_API enum pumas_return pumas_b200_tally_segments(
 /* New: measured FP64 FMA throughput of the current device, in TFLOP/s (the
  * denominator of the roofline fraction reported by bench.py). */
 PUMAS_API enum pumas_return pumas_b200_fp64_peak(double * tflops);
+/* New. Self test of the division / square root of the shared memory resident
+ * kernel (pb_hot_math.h) against the IEEE operations on n random operand
+ * pairs with exponents over +-spread binades (<= 480): the numbers of results
+ * whose bits differ, [0] divisions, [1] square roots. */
+PUMAS_API enum pumas_return pumas_b200_hot_math_selftest(
+    long n, unsigned long seed, int spread, unsigned long long * mismatches);
 
 /* New: 1 when a CUDA device with compute capability 10.x is usable. */
 PUMAS_API int pumas_b200_device_available(void);

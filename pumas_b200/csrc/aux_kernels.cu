@@ -18,6 +18,7 @@
 #include <cmath>
 
 #include "pb_common.h"
+#include "pb_hot_math.h"
 #include "pumas_b200.h"
 
 namespace {
@@ -170,6 +171,85 @@ enum pumas_return pumas_b200_tally(const struct pumas_state * states,
         return (cudaGetLastError() == cudaSuccess) ?
             PUMAS_RETURN_SUCCESS :
             PUMAS_RETURN_INTERNAL_ERROR;
+}
+
+/* Self test of the division and square root of the lean step (pb_hot_math.h:
+ * the fast paths of the IEEE routines without their range checks) against
+ * a / b and sqrt(x) on random operands: mantissas uniform, exponents uniform
+ * over +-`spread` binades (quotients stay inside the stated domain for spread
+ * <= 480), one operand in 64 a zero numerator. mismatches[0]: divisions,
+ * [1]: square roots whose bits differ. */
+namespace {
+__device__ __forceinline__ unsigned long long splitmix(unsigned long long & s)
+{
+        unsigned long long z = (s += 0x9e3779b97f4a7c15ull);
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        return z ^ (z >> 31);
+}
+
+__device__ __forceinline__ double random_operand(
+    unsigned long long & s, int spread)
+{
+        unsigned long long m = splitmix(s);
+        const unsigned long long k = splitmix(s);
+        const int e = (int)((k >> 8) % (unsigned long long)(2 * spread + 1)) -
+            spread;
+        /* one operand in 4 next to a power of two (mantissa 0 + j or all ones
+         * - j, j < 64): where the ties of the roundings live */
+        if ((k & 3ull) == 0)
+                m = (k & 4ull) ? ((k >> 3) & 63ull) :
+                                 (0x000fffffffffffffull - ((k >> 3) & 63ull));
+        const unsigned long long bits = (m & 0x800fffffffffffffull) |
+            ((unsigned long long)(1023 + e) << 52);
+        return __longlong_as_double((long long)bits);
+}
+
+__global__ void hot_math_selftest_kernel(long per_thread,
+    unsigned long long seed, int spread, unsigned long long * mismatches)
+{
+        unsigned long long s = seed +
+            0x632be59bd9b4e019ull *
+                (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x + 1);
+        unsigned long long bad_div = 0, bad_sqrt = 0;
+        for (long i = 0; i < per_thread; i++) {
+                double a = random_operand(s, spread);
+                const double b = random_operand(s, spread);
+                if ((splitmix(s) & 63ull) == 0) a = 0.;
+                const double q = pb::hot_div(a, b), q0 = a / b;
+                if ((__double_as_longlong(q) != __double_as_longlong(q0)) &&
+                    !((q == 0.) && (q0 == 0.)))
+                        bad_div++;
+                const double x = fabs(random_operand(s, 2 * spread));
+                if (__double_as_longlong(pb::hot_sqrt(x)) !=
+                    __double_as_longlong(sqrt(x)))
+                        bad_sqrt++;
+        }
+        if (bad_div) atomicAdd(&mismatches[0], bad_div);
+        if (bad_sqrt) atomicAdd(&mismatches[1], bad_sqrt);
+}
+} /* namespace */
+
+enum pumas_return pumas_b200_hot_math_selftest(
+    long n, unsigned long seed, int spread, unsigned long long * mismatches)
+{
+        if ((mismatches == nullptr) || (n < 0) || (spread < 0) ||
+            (spread > 480))
+                return PUMAS_RETURN_VALUE_ERROR;
+        unsigned long long * d = nullptr;
+        if (cudaMalloc(&d, 2 * sizeof *d) != cudaSuccess)
+                return PUMAS_RETURN_INTERNAL_ERROR;
+        cudaMemset(d, 0, 2 * sizeof *d);
+        const int threads = 256, blocks = 592;
+        const long per_thread = (n + (long)threads * blocks - 1) /
+            ((long)threads * blocks);
+        hot_math_selftest_kernel<<<blocks, threads>>>(
+            per_thread, (unsigned long long)seed, spread, d);
+        const cudaError_t e = cudaMemcpy(
+            mismatches, d, 2 * sizeof *d, cudaMemcpyDeviceToHost);
+        cudaFree(d);
+        return (e == cudaSuccess) ? PUMAS_RETURN_SUCCESS :
+                                    PUMAS_RETURN_INTERNAL_ERROR;
 }
 
 /* Measured FP64 FMA peak of the current device in TFLOP/s (2 flop per FMA). */

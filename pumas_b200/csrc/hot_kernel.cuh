@@ -891,6 +891,18 @@ cudaError_t launch_hot(const Physics & p, const Physics & host_view,
         transport_hot_kernel<Cfg><<<n_service + n_step, HOT_THREADS, smem,
             stream>>>(p, cfg, geo, h, a);
         e = cudaGetLastError();
+#if defined(PB_HOT_MATH_CHECK)
+        {
+                /* (debugging build: every division / square root of the step
+                 * compared with the IEEE operation, pb_hot_math.h) */
+                unsigned long long bad[2] = { 0, 0 };
+                cudaStreamSynchronize(stream);
+                cudaMemcpyFromSymbol(bad, hot_math_mismatches, sizeof bad);
+                fprintf(stderr,
+                    "[hot] math check: %llu divisions, %llu square roots "
+                    "differ from IEEE (cumulated)\n", bad[0], bad[1]);
+        }
+#endif
         if ((e == cudaSuccess) && (t.stats != nullptr)) {
                 unsigned long long hs[N_STATS];
                 cudaMemcpyAsync(hs, t.stats, sizeof hs, cudaMemcpyDeviceToHost,
