@@ -833,6 +833,15 @@ cudaError_t launch_hot(const Physics & p, const Physics & host_view,
         cudaError_t e = cudaFuncSetAttribute(transport_hot_kernel<Cfg>,
             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        {
+                /* experiment: PUMAS_B200_CARVEOUT = shared memory carveout in
+                 * percent of the SM's 228 KB (the rest of 256 KB is L1) */
+                static const char * carve = getenv("PUMAS_B200_CARVEOUT");
+                if (carve != nullptr)
+                        cudaFuncSetAttribute(transport_hot_kernel<Cfg>,
+                            cudaFuncAttributePreferredSharedMemoryCarveout,
+                            atoi(carve));
+        }
         int sms = 0, dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -59,3 +59,23 @@ def test_log_uniform_against_exact():
         ulp = math.ulp(float(exact))
         worst = max(worst, abs(float(Decimal(got) - exact)) / ulp)
     assert worst <= 1.5, worst
+
+
+@pytest.mark.gpu
+def test_division_and_square_root_are_ieee():
+    """hot_div / hot_sqrt (the fast paths of div.rn.f64 / sqrt.rn.f64 without
+    range check and slow path call) give the bits of a / b and sqrt(x): 2^28
+    random pairs per exponent spread, one operand in four next to a power of
+    two (mantissa 0 + j or all ones - j, j < 64: where the ties of the
+    roundings live, e.g. 1 / (1 - 2^-53)), one numerator in 64 zero."""
+    import pumas_b200 as pb
+    assert pb.device_available()
+    lib = pb.library()
+    lib.pumas_b200_hot_math_selftest.argtypes = [
+        ctypes.c_long, ctypes.c_ulong, ctypes.c_int,
+        ctypes.POINTER(ctypes.c_ulonglong)]
+    for spread in (1, 4, 60, 300, 480):
+        bad = (ctypes.c_ulonglong * 2)()
+        assert lib.pumas_b200_hot_math_selftest(
+            1 << 28, 11 + spread, spread, bad) == 0
+        assert (bad[0], bad[1]) == (0, 0), (spread, bad[0], bad[1])
