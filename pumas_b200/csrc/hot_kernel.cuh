@@ -485,6 +485,10 @@ __device__ __noinline__ void hot_service_loop(const Physics & p, const Cfg & cfg
                         const uint32_t index = (uint32_t)idw;
                         rng.seek(
                             a.offset + (uint64_t)index, (uint32_t)(idw >> 32));
+                        /* (the first 12 variates of the event generated by
+                         * the lanes together: inside the DCS code a refill
+                         * runs on 2 lanes) */
+                        rng.top_up();
                         phase = stepping_del(p, cfg, geo, t, rng, st, l);
                         /* (the owner only sees the phase published below,
                          * after the fence) */
@@ -854,12 +858,17 @@ cudaError_t launch_hot(const Physics & p, const Physics & host_view,
          * (straight.c, three times as many hard inelastic events per step)
          * 16 -> 8.3e6, 21 -> 9.4e6, 28 -> 8.8e6 without scattering and
          * 16 -> 5.6e6, 21 -> 6.7e6, 28 -> 6.8e6 with. Below the optimum the
-         * stepping CTAs starve: one SM in 8 forward, one in 6 backward. */
+         * stepping CTAs starve. With the variates of an event generated by
+         * the lanes together (hot_service_loop) the service is cheaper:
+         * headline 12 -> 2.28e6, 14 -> 2.39e6, 16 -> 2.39e6, 18 -> 2.39e6;
+         * rock_3km 16 -> 1.40e6, 21 -> 1.50e6; backward 16 -> 8.3e6, 20 ->
+         * 9.9e6, 24 -> 9.6e6 without scattering and 16 -> 5.8e6, 20 -> 6.9e6,
+         * 24 -> 6.7e6 with: one SM in 8 forward, one in 7 backward. */
         const long per_cta = (long)HOT_CTA_SLOTS;
         const long want = (n + per_cta - 1) / per_cta;
         int n_service = (t.del_ctas > 0) ?
             t.del_ctas :
-            ((Cfg::direction == MODE_FORWARD) ? sms / 8 : sms / 6);
+            ((Cfg::direction == MODE_FORWARD) ? sms / 8 : sms / 7);
         if (n_service > sms - 1) n_service = sms - 1;
         if (n_service < 1) return cudaErrorInvalidConfiguration;
         int n_step = (want < (long)(sms - n_service)) ? (int)want :
