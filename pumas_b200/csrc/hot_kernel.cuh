@@ -121,30 +121,40 @@ extern __shared__ __align__(16) unsigned long long hot_smem64[];
 constexpr unsigned int HOT_SLOTS0 = 2u +
     (unsigned int)(HOT_RING_WORDS * HOT_THREADS * sizeof(uint32_t) / 8);
 constexpr unsigned int HOT_TABLES0 =
-    HOT_SLOTS0 + (unsigned int)(HOT_WORDS * HOT_STRIDE * HOT_WARPS);
+    HOT_SLOTS0 + (unsigned int)(HOT_RESIDENT_WORDS * HOT_STRIDE * HOT_WARPS);
 static_assert((HOT_TABLES0 & 1u) == 0, "16 byte aligned tables");
 
 /* A slot in shared memory: word k at hot_smem64[off + k * HOT_STRIDE] (a 32
  * bit index: one register, and LDS / STS with immediate offsets). */
 struct SmemSlot {
         unsigned int off; /* index of word 0 */
+        /* Words >= HOT_RESIDENT_WORDS (weight, ti, wi, Xf, dei: read and
+         * written by events only) stay in the slot's mirror in HBM / L2:
+         * 15 words per slot instead of 20 leave 92 KB of L1 to the packed
+         * tables and the register saves instead of 60 (+5 % tracks/s,
+         * profiles/r2_experiments.md section 11). `k` is a constant at every
+         * call site: the test folds away. */
+        unsigned long long * cold; /* word 0 of the mirror of this slot */
         __device__ __forceinline__ double ld(int k) const
         {
-                return __longlong_as_double(
-                    (long long)hot_smem64[off + k * HOT_STRIDE]);
+                return __longlong_as_double((long long)ldu(k));
         }
         __device__ __forceinline__ void st(int k, double v)
         {
-                hot_smem64[off + k * HOT_STRIDE] =
-                    (unsigned long long)__double_as_longlong(v);
+                stu(k, (unsigned long long)__double_as_longlong(v));
         }
         __device__ __forceinline__ unsigned long long ldu(int k) const
         {
+                if (k >= HOT_RESIDENT_WORDS)
+                        return __ldcg(&cold[(size_t)k * HOT_STRIDE]);
                 return hot_smem64[off + k * HOT_STRIDE];
         }
         __device__ __forceinline__ void stu(int k, unsigned long long v)
         {
-                hot_smem64[off + k * HOT_STRIDE] = v;
+                if (k >= HOT_RESIDENT_WORDS)
+                        __stcg(&cold[(size_t)k * HOT_STRIDE], v);
+                else
+                        hot_smem64[off + k * HOT_STRIDE] = v;
         }
 };
 
@@ -614,7 +624,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 1)
 #endif
                 __syncthreads();
                 const unsigned int mine = SLOTS0 +
-                    (unsigned int)warp * (HOT_WORDS * HOT_STRIDE) +
+                    (unsigned int)warp * (HOT_RESIDENT_WORDS * HOT_STRIDE) +
                     (unsigned int)lane;
                 unsigned long long * const mirror =
                     hot_mirror(a.workspace, cta, warp, lane);
@@ -669,9 +679,11 @@ __global__ void __launch_bounds__(HOT_THREADS, 1)
                                                 if (ph == PHASE_STEP) {
                                                         SmemSlot s;
                                                         s.off = mine + 32u * j;
-#pragma unroll 4
+                                                        s.cold = mirror + 32 * j;
+#pragma unroll 5
                                                         for (int k = 0;
-                                                             k < HOT_WORDS; k++)
+                                                             k < HOT_RESIDENT_WORDS;
+                                                             k++)
                                                                 s.stu(k,
                                                                     m.ldu(k));
                                                 } else {
@@ -730,6 +742,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 1)
                                 if (je >= 0) {
                                         SmemSlot s;
                                         s.off = mine + 32u * je;
+                                        s.cold = mirror + 32 * je;
                                         if (attached != je) {
                                                 const unsigned long long idw =
                                                     s.ldu(HF_ID);
@@ -767,6 +780,7 @@ __global__ void __launch_bounds__(HOT_THREADS, 1)
                         if (js >= 0) {
                                 SmemSlot s;
                                 s.off = mine + 32u * js;
+                                s.cold = mirror + 32 * js;
                                 if (attached != js) {
                                         const unsigned long long idw =
                                             s.ldu(HF_ID);
@@ -795,10 +809,12 @@ __global__ void __launch_bounds__(HOT_THREADS, 1)
                                         (phase[j] == PHASE_DONE))) {
                                         SmemSlot s;
                                         s.off = mine + 32u * j;
+                                        s.cold = mirror + 32 * j;
                                         MirrorSlot m;
                                         m.base = mirror + 32 * j;
-#pragma unroll 4
-                                        for (int k = 0; k < HOT_WORDS; k++)
+#pragma unroll 5
+                                        for (int k = 0; k < HOT_RESIDENT_WORDS;
+                                             k++)
                                                 m.stu(k, s.ldu(k));
                                         __threadfence();
                                         hot_queue_push(

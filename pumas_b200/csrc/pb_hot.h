@@ -218,7 +218,6 @@ enum {
         HF_DISTANCE,
         HF_GRAMMAGE,
         HF_TIME,
-        HF_WEIGHT,
         HF_PX,
         HF_PY,
         HF_PZ,
@@ -227,13 +226,17 @@ enum {
         HF_UZ,
         HF_INVLB1, /* Track::step_invlb1 */
         HF_RANDN,  /* Track::randn_next */
+        HF_T0,     /* reduced abscissa of the energy in cell iK, when located */
+        HF_FLAGS,  /* packed flags (low) and n_steps (high) */
+        HF_ID,     /* position in the batch (low) and variates drawn (high) */
+        /* the words only events touch (1 step in 6): the kernel keeps them in
+         * the HBM mirror of the slot instead of shared memory */
+        HOT_RESIDENT_WORDS,
+        HF_WEIGHT = HOT_RESIDENT_WORDS,
         HF_TI,     /* Loop::ti */
         HF_WI,     /* Loop::wi */
         HF_XF,     /* Loop::Xf  (backward weights) */
         HF_DEI,    /* Loop::dei (backward weights) */
-        HF_T0,     /* reduced abscissa of the energy in cell iK, when located */
-        HF_FLAGS,  /* packed flags (low) and n_steps (high) */
-        HF_ID,     /* position in the batch (low) and variates drawn (high) */
         HOT_WORDS
 };
 
