@@ -1,0 +1,3 @@
+#!/bin/bash
+run() { PUMAS_B200_LIBRARY=$PWD/pumas_b200/$1 timeout -s KILL 100 python tests/_gpu_variant.py $2 1000000 2 2>&1 | tail -1; }
+for w in headline straight_mixed; do for v in libpumas_b200_before.so libpumas_b200.so libpumas_b200_logout.so; do run $v $w; done; done
