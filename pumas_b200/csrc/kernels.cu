@@ -128,6 +128,7 @@ PB_SPECIALISATION(launch_spec_straggled_mixed_forward);
 PB_SPECIALISATION(launch_spec_straggled_mixed_backward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_forward);
 PB_SPECIALISATION(launch_spec_straggled_noscat_backward);
+PB_SPECIALISATION(launch_spec_geo_straggled_mixed_backward);
 bool launch_spec_csda(const Physics & p, const Physics & host_view,
     const Settings & cfg, const Geometry & geo, uint64_t seed, uint64_t offset,
     long n, State * states, int * events, int * media, int * status,
@@ -197,6 +198,8 @@ cudaError_t launch_transport(const Physics & p, const Physics & host_view,
                 TRY(launch_spec_straggled_mixed_backward)
                 TRY(launch_spec_straggled_noscat_forward)
                 TRY(launch_spec_straggled_noscat_backward)
+                /* (any descriptor geometry) */
+                TRY(launch_spec_geo_straggled_mixed_backward)
 #undef TRY
         }
         /* KERNEL_RESIDENT_GENERAL, or no specialisation applies. */

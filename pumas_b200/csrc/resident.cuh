@@ -1551,6 +1551,19 @@ inline bool geometry_is_plain_uniform(const Geometry & geo)
                 return true;                                                   \
         }
 
+/* The same for any descriptor geometry (layers, locals, magnetic field): only
+ * the settings are compile time constants. */
+#define PB_DEFINE_SPECIALISATION_GEO(NAME, EL, SC, DI, DE)                     \
+        PB_SPECIALISATION(NAME)                                                \
+        {                                                                      \
+                typedef StaticSettings<EL, SC, DI, DE> Cfg;                    \
+                if (!Cfg::matches(cfg)) return false;                          \
+                *error = launch_resident(p, Cfg(cfg), geo, seed, offset, n,    \
+                    states, events, media, status, n_random, n_steps,          \
+                    workspace, stream);                                        \
+                return true;                                                   \
+        }
+
 } /* namespace pb */
 
 #endif
