@@ -195,6 +195,12 @@ EXTRA = [
     ("geometry_grid", 48 * 8192, "fp64", 600.),   # configs[3], 6 x 8 grid
     ("tau_ice", 1 << 21, "fp64", 600.),           # configs[4]
 ]
+# pumas_b200_context_kernel_set (public knob): tracks of a few Monte Carlo steps
+# (tau_ice: 3) spend their time entering and leaving the engine; the register
+# resident kernel starts them in the stepping CTAs instead of the service CTAs
+# of the shared memory resident kernel (B200, 4 M tracks: 7.2e6 against 5.6e6
+# tracks/s; results within 1e-9 of the reference with either).
+EXTRA_KERNEL = {"tau_ice": 3}
 
 
 def measured_hbm_peak():
@@ -223,6 +229,8 @@ def run_extra(pb, harness, WORKLOADS, torch, np, peak_tflops):
             ctx.configure(w["settings"])
             ctx.geometry(w["geometry"])
             ctx.stream(stream.cuda_stream)
+            if name in EXTRA_KERNEL:
+                ctx.kernel(EXTRA_KERNEL[name])
             pristine = torch.from_numpy(
                 w["states"].view(np.uint8).reshape(n, 104).copy()).cuda()
             work = torch.empty_like(pristine)
@@ -244,7 +252,8 @@ def run_extra(pb, harness, WORKLOADS, torch, np, peak_tflops):
             t = sorted(ms)[len(ms) // 2] * 1e-3
             row = {"tracks_per_s": n / t, "tracks_per_launch": n,
                    "launch_ms": [round(x, 3) for x in ms],
-                   "steps_per_track": steps, "bound": bound}
+                   "steps_per_track": steps, "bound": bound,
+                   "kernel": EXTRA_KERNEL.get(name, 0)}
             if bound == "hbm":
                 row["achieved_GBps"] = unit_cost * n / t * 1e-9
                 row["peak_GBps"] = hbm
