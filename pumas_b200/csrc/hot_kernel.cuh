@@ -314,6 +314,19 @@ __device__ __forceinline__ unsigned long long * hot_mirror(
             ((size_t)cta * HOT_WARPS + warp) * HOT_WORDS * HOT_STRIDE + e;
 }
 
+/* Watchdog: a scheduler that makes no progress for HOT_WATCHDOG_NS (a lost
+ * slot: nothing queued, the batch not over) must not hang the device; the
+ * kernel traps and the call returns PUMAS_RETURN_INTERNAL_ERROR. The longest
+ * legitimate wait is one track's hard event (seconds for the runaway backward
+ * tracks of profiles/r2_experiments.md section 7). */
+constexpr unsigned long long HOT_WATCHDOG_NS = 30000000000ull;
+__device__ __forceinline__ unsigned long long hot_now_ns()
+{
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        return t;
+}
+
 /* CTA wide control block of a stepping CTA. */
 struct HotShared {
         int retired; /* slots of this CTA retired so far */
@@ -446,6 +459,7 @@ __device__ __noinline__ void hot_service_loop(const Physics & p, const Cfg & cfg
         volatile unsigned int * const queue =
             reinterpret_cast<volatile unsigned int *>(a.workspace + HOT_Q_OFFSET);
         int idle = 0;
+        unsigned long long idle_since = 0;
         for (;;) {
                 __syncwarp();
                 int avail = 0, over = 0;
@@ -461,9 +475,22 @@ __device__ __noinline__ void hot_service_loop(const Physics & p, const Cfg & cfg
                 if ((avail <= 0) || ((avail < a.del_threshold) && (idle < a.service_patience))) {
                         __nanosleep(2000);
                         idle++;
+                        if ((lane == 0) && ((idle & 1023) == 0)) {
+                                const unsigned long long now = hot_now_ns();
+                                if (idle_since == 0)
+                                        idle_since = now;
+                                else if (now - idle_since > HOT_WATCHDOG_NS) {
+                                        printf("[hot] service warp idle for "
+                                               "30 s with the batch not over: "
+                                               "retired %d of %d slots\n",
+                                            g->retired, g->n_slots);
+                                        __trap();
+                                }
+                        }
                         continue;
                 }
                 idle = 0;
+                idle_since = 0;
                 const unsigned int id =
                     hot_queue_pop(g, queue, (avail < 32) ? avail : 32, lane);
                 const bool have = (id != HOT_NONE);

@@ -136,19 +136,29 @@ PB_FN void del_randomise_target(const Physics & p, const Cfg & cfg,
         info->process = N_DEL_PROCESSES - 1;
 }
 
-/* pumas.c:5912-6017. Returns true when a polar angle must be sampled for
- * (*process, *element); false is the reference's NULL polar function. */
+/* pumas.c:5912-6017 in two parts (a scheduler may regroup the events by
+ * process between them; tried and rejected on B200, profiles/r2_experiments.md
+ * section 13): the threshold test and the choice of the target (false: below
+ * the threshold, no event), then the sampling of the energy transfer for that
+ * target. Returns true when a polar angle must be sampled for (*process,
+ * *element); false is the reference's NULL polar function. */
 template <class Cfg, class Rng>
-PB_FN bool del_randomise_forward(const Physics & p, const Cfg & cfg,
-    Rng & rng, State & state, int material, int * process, int * element)
+PB_FN bool del_forward_target(const Physics & p, const Cfg & cfg, Rng & rng,
+    const State & state, int material, DelInfo * info)
 {
         if (state.energy <= p.Kt[material]) return false;
+        info->reverse = 0.;
+        info->process = 0;
+        info->element = 0;
+        del_randomise_target(p, cfg, rng, state, material, info);
+        return true;
+}
 
-        DelInfo info;
-        info.reverse = 0.;
-        info.process = 0;
-        info.element = 0;
-        del_randomise_target(p, cfg, rng, state, material, &info);
+template <class Cfg, class Rng>
+PB_FN bool del_forward_sample(const Physics & p, const Cfg & cfg, Rng & rng,
+    State & state, const DelInfo & info, int * process, int * element)
+{
+        (void)cfg;
         const Element & el = p.element[info.element];
         *element = info.element;
         *process = info.process;
@@ -233,6 +243,16 @@ PB_FN bool del_randomise_forward(const Physics & p, const Cfg & cfg,
                 state.energy *= (1. - x);
                 return true;
         }
+}
+
+template <class Cfg, class Rng>
+PB_FN bool del_randomise_forward(const Physics & p, const Cfg & cfg,
+    Rng & rng, State & state, int material, int * process, int * element)
+{
+        DelInfo info;
+        if (!del_forward_target(p, cfg, rng, state, material, &info))
+                return false;
+        return del_forward_sample(p, cfg, rng, state, info, process, element);
 }
 
 /* pumas.c:6109-6138 */

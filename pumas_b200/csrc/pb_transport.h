@@ -291,27 +291,13 @@ PB_FN void transport_limit(const Physics & p, const Cfg & cfg, Track & trk,
         }
 }
 
-/* pumas.c:5706-5757 */
+/* pumas.c:5723-5757: the event flag of a hard inelastic vertex and its polar
+ * deflection. */
 template <class Cfg, class Rng>
-PB_FN void transport_do_del(const Physics & p, const Cfg & cfg,
-    Track & trk, Rng & rng, State & state, int material)
+PB_FN void transport_do_del_tail(const Physics & p, const Cfg & cfg,
+    Track & trk, Rng & rng, State & state, int process, int element,
+    bool polar, double ki, double kf)
 {
-        double ki, kf;
-        int process = -1;
-        int element = 0;
-        bool polar;
-        if (cfg.direction == MODE_FORWARD) {
-                ki = state.energy;
-                polar = del_randomise_forward(
-                    p, cfg, rng, state, material, &process, &element);
-                kf = state.energy;
-        } else {
-                kf = state.energy;
-                polar = del_randomise_reverse(
-                    p, cfg, rng, state, material, &process, &element);
-                ki = state.energy;
-        }
-
         if (process < 0) {
                 if (state.weight > 0)
                         trk.step_event = EVENT_NONE;
@@ -337,6 +323,30 @@ PB_FN void transport_do_del(const Physics & p, const Cfg & cfg,
                     polar_sample(p, rng, process, p.element[element], ki, kf);
                 step_rotate_direction(rng, state, mu);
         }
+}
+
+/* pumas.c:5706-5757 */
+template <class Cfg, class Rng>
+PB_FN void transport_do_del(const Physics & p, const Cfg & cfg,
+    Track & trk, Rng & rng, State & state, int material)
+{
+        double ki, kf;
+        int process = -1;
+        int element = 0;
+        bool polar;
+        if (cfg.direction == MODE_FORWARD) {
+                ki = state.energy;
+                polar = del_randomise_forward(
+                    p, cfg, rng, state, material, &process, &element);
+                kf = state.energy;
+        } else {
+                kf = state.energy;
+                polar = del_randomise_reverse(
+                    p, cfg, rng, state, material, &process, &element);
+                ki = state.energy;
+        }
+        transport_do_del_tail(
+            p, cfg, trk, rng, state, process, element, polar, ki, kf);
 }
 
 /* Restricted (hard) cross-section of one component, pumas.c:5786-5813. */
