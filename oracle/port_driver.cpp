@@ -294,6 +294,89 @@ int port_transport_n(const void * physics, const struct pumas_context * settings
         return rc;
 }
 
+/* ---- the callback interface on the CPU build --------------------------------
+ * CallbackGeometry (pb_media.h) with HOST functions: the user media of
+ * examples/user_media.h, the same header the device build and the reference's
+ * host callbacks (oracle_driver.c) compile. tests/test_port_vs_reference.py
+ * compares this path with the reference bit for bit. */
+#include "../examples/user_media.h"
+
+static int port_user_medium_fn(const void * user_data,
+    const struct pumas_state * state, int backward, int * medium, double * step)
+{
+        return user_media_locate(static_cast<const struct user_media *>(user_data),
+            state->position, state->direction, backward, medium, step);
+}
+
+static double port_user_locals_fn(const void * user_data, int medium,
+    const struct pumas_state * state, double * density, double * magnet)
+{
+        magnet[0] = magnet[1] = magnet[2] = 0.;
+        return user_media_density(
+            static_cast<const struct user_media *>(user_data), medium,
+            state->position, density);
+}
+
+int port_transport_user_media(const void * physics,
+    const struct pumas_context * settings, const struct user_media * shells,
+    const int * materials, uint64_t seed, uint64_t offset, long n,
+    struct pumas_state * states, int * events, int * media,
+    unsigned int * n_random, unsigned int * n_steps)
+{
+        const pb::HostPhysics * hp = static_cast<const pb::HostPhysics *>(physics);
+        const pb::Settings cfg = settings_from(settings);
+        const int rc0 = pb::settings_check(hp->view, cfg);
+        if (rc0 != 0) return rc0;
+        pb::CallbackGeometry geo;
+        memset(&geo, 0x0, sizeof geo);
+        geo.cb.medium = &port_user_medium_fn;
+        geo.cb.locals = &port_user_locals_fn;
+        geo.cb.user_data = shells;
+        geo.cb.n_media = shells->n_shells;
+        for (int i = 0; i < shells->n_shells; i++) {
+                geo.cb.material[i] = materials[i];
+                geo.cb.has_locals[i] = 1;
+        }
+        Job job;
+        job.hp = hp;
+        job.cfg = cfg;
+        job.geo = NULL;
+        job.seed = seed;
+        job.offset = offset;
+        job.begin = 0;
+        job.end = n;
+        job.states = reinterpret_cast<pb::State *>(states);
+        job.events = events;
+        job.media = media;
+        job.n_random = n_random;
+        job.n_steps = n_steps;
+        job.rc = 0;
+        run_tracks(&job, cfg, geo);
+        return job.rc;
+}
+
+/* ---- a user DCS model on the CPU build (examples/user_dcs.h) -------------- */
+#include "../examples/user_dcs.h"
+
+static double port_user_dcs(double Z, double A, double m, double K, double q)
+{
+        return user_dcs_bremsstrahlung(Z, A, m, K, q);
+}
+
+/* Resolve the user models of a loaded physics (what pumas_physics_load of the
+ * library does against its registry). Returns the number resolved. */
+int port_register_user_dcs(void * physics)
+{
+        pb::HostPhysics * hp = static_cast<pb::HostPhysics *>(physics);
+        int n = 0;
+        if ((hp->view.model[0] == pb::MODEL_USER) &&
+            (hp->model[0] == USER_DCS_MODEL)) {
+                hp->view.user_dcs[0] = &port_user_dcs;
+                n++;
+        }
+        return n;
+}
+
 /* Function level hooks, mirroring oracle_driver.c. */
 double port_dcs_evaluate(
     const void * physics, int process, int element, double K, double q)

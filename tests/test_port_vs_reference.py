@@ -156,3 +156,107 @@ def test_hard_elastic_cross_sections_double_double():
     assert worst_x87 < 1e-4, worst_x87
     if quad is not None:
         assert worst_dd < 1e-15, worst_dd
+
+
+def test_user_media_callbacks_bit_exact():
+    """The callback interface of the engine (CallbackGeometry, pb_media.h) on
+    the CPU build with host functions -- the spherical shells of
+    examples/user_media.h -- against the reference driving the same header
+    through its own host callbacks: bit for bit (same libm on both sides).
+    The GPU runs the same engine code with `__device__` functions
+    (tests/test_callbacks.py)."""
+    import ctypes
+    import _user_media_run as um
+    import pumas_b200 as pb
+    from workloads import isotropic, log_uniform
+    oracle, port, _ = sides("materials.muon")
+    g, materials = um.shells(oracle.material)
+    oracle.lib.oracle_set_user_media.argtypes = [
+        ctypes.POINTER(um.UserMedia), ctypes.POINTER(ctypes.c_int)]
+    f = port.lib.port_transport_user_media
+    f.argtypes = [
+        ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(um.UserMedia),
+        ctypes.POINTER(ctypes.c_int), ctypes.c_uint64, ctypes.c_uint64,
+        ctypes.c_long, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+        ctypes.c_void_p, ctypes.c_void_p]
+    n = 3000
+    cases = [
+        (harness.make_settings(pb.MODE_STRAGGLED, pb.MODE_MIXED),
+         pb.make_states(n, log_uniform(n, 0.5, 200., 1),
+                        direction=isotropic(n, 2), position=(10., 5., -20.))),
+        (harness.make_settings(pb.MODE_STRAGGLED, pb.MODE_MIXED,
+                               direction=pb.MODE_BACKWARD,
+                               event=pb.EVENT_LIMIT_ENERGY, limit_energy=1e3),
+         pb.make_states(n, log_uniform(n, 0.5, 50., 3),
+                        direction=isotropic(n, 4), position=(10., 5., -20.))),
+        (harness.make_settings(pb.MODE_CSDA, pb.MODE_DISABLED),
+         pb.make_states(n, log_uniform(n, 0.5, 200., 5),
+                        direction=isotropic(n, 6), position=(0., 60., 0.))),
+        (harness.make_settings(pb.MODE_MIXED, pb.MODE_MIXED,
+                               event=pb.EVENT_MEDIUM),
+         pb.make_states(n, log_uniform(n, 5., 500., 7),
+                        direction=isotropic(n, 8), position=(0., 0., 45.))),
+    ]
+    try:
+        oracle.lib.oracle_set_user_media(ctypes.byref(g), materials)
+        for settings, states in cases:
+            so, eo, mo, ro, rc, _ = oracle.transport(
+                settings, pb.uniform_geometry(0), states, seed=11, offset=500,
+                threads=THREADS)
+            assert rc == 0
+            sp = np.ascontiguousarray(states.copy())
+            ep = np.zeros(n, dtype=np.int32)
+            mp = np.zeros((n, 2), dtype=np.int32)
+            rp = np.zeros(n, dtype=np.uint32)
+            steps = np.zeros(n, dtype=np.uint32)
+            assert f(port.physics, ctypes.byref(settings), ctypes.byref(g),
+                     materials, 11, 500, n, sp.ctypes.data, ep.ctypes.data,
+                     mp.ctypes.data, rp.ctypes.data, steps.ctypes.data) == 0
+            c = harness.compare_states(so, sp, eo, ep, ro, rp)
+            assert c["n_diverged"] == 0
+            assert c["n_bitexact"] == n, c["max_rel"]
+            assert np.array_equal(mo, mp)
+            assert ((ep & pb.EVENT_MEDIUM) != 0).any() or (mp[:, 1] < 0).any()
+    finally:
+        oracle.lib.oracle_set_user_media(None, None)
+
+
+def test_user_dcs_bit_exact():
+    """A user registered DCS model (examples/user_dcs.h; tables made by the
+    reference with it) evaluated by the engine through Physics::user_dcs, CPU
+    build against the reference: bit for bit."""
+    import ctypes
+    from workloads import dcs_models
+    import pumas_b200 as pb
+    if not (harness.have_oracle() and harness.have_port()):
+        pytest.skip("oracle/_ref or oracle/_port not built")
+    lib_o = ctypes.CDLL(harness.ORACLE_SO)
+    assert lib_o.oracle_register_user_dcs() == 0
+    oracle = harness.Oracle("rock.muon.usr")
+    port = harness.Port("rock.muon.usr")
+    port.lib.port_register_user_dcs.argtypes = [ctypes.c_void_p]
+    assert port.lib.port_register_user_dcs(port.physics) == 1
+    # the model itself, then the transport that calls it
+    K = np.logspace(-1, 6, 29)
+    for k in K:
+        for x in (1e-3, 0.05, 0.5, 0.9):
+            a = oracle.lib.oracle_dcs_model(oracle.physics, 0, 0, k, x * k)
+            b = port.lib.port_dcs_model(port.physics, 0, 0, k, x * k)
+            assert a == b, (k, x, a, b)
+    n = 2000
+    for direction in (pb.MODE_FORWARD, pb.MODE_BACKWARD):
+        w = dcs_models(oracle.material, n, direction=direction)
+        so, eo, mo, ro, rc, _ = oracle.transport(
+            w["settings"], w["geometry"], w["states"], seed=13, offset=900,
+            threads=THREADS)
+        assert rc == 0
+        for specialise in (1, 0):
+            port.lib.port_set_specialise(specialise)
+            sp, ep, mp, rp, steps, rcp = port.transport(
+                w["settings"], w["geometry"], w["states"], seed=13,
+                offset=900, threads=THREADS)
+            assert rcp == 0
+            c = harness.compare_states(so, sp, eo, ep, ro, rp)
+            assert c["n_diverged"] == 0
+            assert c["n_bitexact"] == n, c["max_rel"]
+    port.lib.port_set_specialise(1)
