@@ -17,9 +17,8 @@
 
 namespace pb {
 
-/* One Philox4x32-10 block, out of line (one copy instead of one per call site
- * of uniform()). */
-static __device__ __noinline__ uint4 philox_block(
+/* One Philox4x32-10 block. */
+static __device__ __forceinline__ uint4 philox_block_inline(
     uint32_t key0, uint32_t key1, uint32_t block, uint32_t trk0, uint32_t trk1)
 {
         uint32_t c0 = block, c1 = 0, c2 = trk0, c3 = trk1;
@@ -38,6 +37,13 @@ static __device__ __noinline__ uint4 philox_block(
                 k1 += 0xBB67AE85u;
         }
         return make_uint4(c0, c1, c2, c3);
+}
+
+/* The same out of line (one copy instead of one per call site of uniform()). */
+static __device__ __noinline__ uint4 philox_block(
+    uint32_t key0, uint32_t key1, uint32_t block, uint32_t trk0, uint32_t trk1)
+{
+        return philox_block_inline(key0, key1, block, trk0, trk1);
 }
 
 /* Philox4x32-10 stream of one track, register resident. Same stream as

@@ -226,8 +226,13 @@ struct HotRng {
                         const bool need =
                             (int)(filled - count) <= (HOT_RING_WORDS - 5);
                         if (!__any_sync(__activemask(), need)) break;
+#if defined(PB_HOT_OUTLINE_CALLS)
                         const uint4 o =
                             philox_block(key0, key1, filled >> 2, trk0, trk1);
+#else
+                        const uint4 o = philox_block_inline(
+                            key0, key1, filled >> 2, trk0, trk1);
+#endif
                         if (need) put(o);
                 }
         }

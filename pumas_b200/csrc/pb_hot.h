@@ -450,6 +450,15 @@ PB_FN bool hot_energy_ok(const HotCtx & h, double k)
  * energy at the grammage of the candidate vertex, located in the grid when it
  * lies there. One out of line copy for the two call sites; the look-ups walk
  * from the cell of the start energy (the candidate lies within the step). */
+/* In line since the loop's footprint stopped being what bounds the kernel
+ * (profiles/r2_experiments.md sections 12, 14): a call saves and restores the
+ * live registers through local memory. -DPB_HOT_OUTLINE_CALLS: the one-copy
+ * versions of rounds 1 and 2 (A/B). */
+#if defined(PB_HOT_OUTLINE_CALLS)
+#define PB_HOT_VERTEX_CALL PB_NOINLINE
+#else
+#define PB_HOT_VERTEX_CALL PB_FN
+#endif
 struct HotVertex {
         double k;
         HLoc l;
@@ -457,7 +466,7 @@ struct HotVertex {
 };
 
 template <class Cfg>
-PB_NOINLINE HotVertex hot_vertex(const Physics & p, const Cfg & cfg,
+PB_HOT_VERTEX_CALL HotVertex hot_vertex(const Physics & p, const Cfg & cfg,
     const HotCtx & h, double energy, double Xtot, double X_ev, double ratio,
     int hint)
 {
@@ -1057,8 +1066,13 @@ PB_NOINLINE int hot_ehs_general(const Physics & p, const Cfg & cfg,
  * Only the energy and the direction of the track take part in the event; the
  * rest of the slot is touched by the re-arming alone.
  */
+#if defined(PB_HOT_OUTLINE_CALLS)
+#define PB_HOT_EHS_CALL PB_NOINLINE
+#else
+#define PB_HOT_EHS_CALL PB_FN
+#endif
 template <class Cfg, class S, class Rng>
-PB_NOINLINE int hot_ehs(const Physics & p, const Cfg & cfg,
+PB_HOT_EHS_CALL int hot_ehs(const Physics & p, const Cfg & cfg,
     const UniformGeometry & geo, const HotCtx & h, S & s, Rng & rng)
 {
         constexpr bool forward = (Cfg::direction == MODE_FORWARD);
