@@ -1001,7 +1001,7 @@ PB_FN int hot_step(const Physics & p, const Cfg & cfg,
         int phase = PHASE_STEP;
         if (event != EVENT_NONE) {
                 /* weights, pumas.c:5309-5321 */
-                const double wt = xexp(
+                const double wt = hot_exp(
                     hot_div(-fabs(s.ld(HF_TIME) - s.ld(HF_TI)), h.ctau));
                 if (!forward) {
                         double de;
