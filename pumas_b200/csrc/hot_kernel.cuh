@@ -322,9 +322,10 @@ __device__ __forceinline__ unsigned long long * hot_mirror(
 /* Watchdog: a scheduler that makes no progress for HOT_WATCHDOG_NS (a lost
  * slot: nothing queued, the batch not over) must not hang the device; the
  * kernel traps and the call returns PUMAS_RETURN_INTERNAL_ERROR. The longest
- * legitimate wait is one track's hard event (seconds for the runaway backward
- * tracks of profiles/r2_experiments.md section 7). */
-constexpr unsigned long long HOT_WATCHDOG_NS = 30000000000ull;
+ * legitimate wait is one track's hard event: 2.4 s for the runaway backward
+ * tracks of profiles/r2_experiments.md section 7 (4 million variates), hence
+ * two minutes. */
+constexpr unsigned long long HOT_WATCHDOG_NS = 120000000000ull;
 __device__ __forceinline__ unsigned long long hot_now_ns()
 {
         unsigned long long t;
@@ -486,7 +487,7 @@ __device__ __noinline__ void hot_service_loop(const Physics & p, const Cfg & cfg
                                         idle_since = now;
                                 else if (now - idle_since > HOT_WATCHDOG_NS) {
                                         printf("[hot] service warp idle for "
-                                               "30 s with the batch not over: "
+                                               "120 s with the batch not over: "
                                                "retired %d of %d slots\n",
                                             g->retired, g->n_slots);
                                         __trap();
