@@ -200,3 +200,75 @@ def test_user_dcs_vs_reference():
         assert c["diverged"] <= 2e-3 * c["n"], (name, c)
         assert c["off_in_sync"] <= 2e-3 * c["n"], (name, c)
         assert c["match"] >= 0.998 * c["n"], (name, c)
+
+
+def _build_shells(tmp_path):
+    import shutil
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    so = _user_library()
+    exe = str(tmp_path / "shells_b200")
+    subprocess.run(
+        ["gcc", "-std=c99", "-D_DEFAULT_SOURCE", "-Wall", "-Wextra", "-Werror",
+         os.path.join(ROOT, "examples", "shells_b200.c"),
+         "-I" + os.path.join(ROOT, "include"),
+         "-I" + os.path.join(ROOT, "examples"),
+         "-L" + os.path.dirname(so), "-lpumas_b200_user", "-lm",
+         "-Wl,-rpath," + os.path.dirname(so), "-o", exe], check=True)
+    return exe
+
+
+def test_c_program_on_user_media_links(tmp_path):
+    """examples/shells_b200.c: a C user program against include/*.h and the
+    user's device-linked library."""
+    exe = _build_shells(tmp_path)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode != 0 and "usage" in r.stderr
+
+
+@pytest.mark.gpu
+def test_c_program_on_user_media_matches_python_binding(tmp_path):
+    import re
+    exe = _build_shells(tmp_path)
+    n, kinetic = 10000, 150.
+    r = subprocess.run([exe, harness.dump_path("materials.muon"), str(n),
+                        str(kinetic)], capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr
+    left = int(re.search(r"Left\s+: (\d+)", r.stdout).group(1))
+    stopped = [int(x) for x in re.search(
+        r"Stopped : (\d+) in rock, (\d+) in water, (\d+) in air",
+        r.stdout).groups()]
+    path = float(re.search(r"Path\s+: (\S+) m", r.stdout).group(1))
+    assert left + sum(stopped) == n and left > 0 and sum(stopped) > 0
+
+    code = r"""
+import ctypes, sys
+sys.path.insert(0, 'tests')
+import numpy as np
+import harness, pumas_b200 as pb
+import _user_media_run as um
+n, kinetic = %d, %r
+physics = pb.Physics(harness.dump_path('materials.muon'))
+g, materials = um.shells(physics.material_index)
+lib = pb.library()
+cb = pb.Callbacks()
+lib.user_media_callbacks.argtypes = [ctypes.POINTER(um.UserMedia),
+    ctypes.POINTER(ctypes.c_int), ctypes.POINTER(pb.Callbacks)]
+assert lib.user_media_callbacks(ctypes.byref(g), materials, ctypes.byref(cb)) == 0
+ctx = pb.Context(physics, seed=1)
+ctx.configure(harness.make_settings(pb.MODE_STRAGGLED, pb.MODE_MIXED))
+ctx.callbacks(cb)
+phi = 2. * np.pi * (np.arange(n) + 0.5) / n
+d = np.stack([np.cos(phi), np.zeros(n), np.sin(phi)], axis=1)
+s = pb.make_states(n, kinetic, direction=d, position=(10., 5., -20.))
+ev, md = ctx.transport(s)
+print(int((md[:, 1] < 0).sum()), '%%.6f' %% s['distance'].mean())
+""" % (n, kinetic)
+    env = dict(os.environ, PUMAS_B200_LIBRARY=_user_library())
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True,
+                         text=True, env=env, cwd=ROOT, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    left_py, path_py = out.stdout.split()
+    assert int(left_py) == left
+    assert abs(float(path_py) - path) <= 2e-6
