@@ -102,7 +102,8 @@ void run_tracks_hot(Job * job, const Cfg & cfg, const pb::UniformGeometry & geo)
         using namespace pb;
         const Physics & p = job->hp->view;
         /* (the packed tables the dump loader built) */
-        const HotCtx h = hot_context(p, p, p.hotK, p.hotX, cfg, geo.material);
+        const HotCtx h = hot_context(
+            p, p, p.hotK, p.hotX, cfg, geo.material, geo.density);
         for (long i = job->begin; i < job->end; i++) {
                 PhiloxRng rng;
                 pb_philox_init(&rng.g, job->seed, job->offset + (uint64_t)i);
@@ -152,7 +153,7 @@ void run_tracks_csda(Job * job, const Cfg & cfg, const pb::UniformGeometry & geo
 {
         using namespace pb;
         const Physics & p = job->hp->view;
-        const CsdaCtx c = csda_context(p, p, cfg, geo.material);
+        const CsdaCtx c = csda_context(p, p, cfg, geo.material, geo.density);
         for (long i = job->begin; i < job->end; i++) {
                 PhiloxRng rng;
                 pb_philox_init(&rng.g, job->seed, job->offset + (uint64_t)i);
@@ -178,12 +179,9 @@ template <int DI> bool try_csda(Job * job)
             pb::MODE_WEIGHTED>
             Cfg;
         const pumas_b200_geometry & geo = *job->geo;
-        if (!Cfg::matches(job->cfg) ||
-            (geo.kind != PUMAS_B200_GEOMETRY_UNIFORM) || geo.layer[0].has_locals)
-                return false;
         pb::UniformGeometry ug;
-        ug.material = geo.layer[0].material;
-        ug.step_type = geo.step_type;
+        if (!Cfg::matches(job->cfg) || !pb::uniform_geometry_of(geo, &ug))
+                return false;
         run_tracks_csda(job, Cfg(job->cfg), ug);
         return true;
 }
@@ -192,12 +190,9 @@ template <int EL, int SC, int DI, int DE> bool try_specialised(Job * job)
 {
         typedef pb::StaticSettings<EL, SC, DI, DE> Cfg;
         const pumas_b200_geometry & geo = *job->geo;
-        if (!Cfg::matches(job->cfg) ||
-            (geo.kind != PUMAS_B200_GEOMETRY_UNIFORM) || geo.layer[0].has_locals)
-                return false;
         pb::UniformGeometry ug;
-        ug.material = geo.layer[0].material;
-        ug.step_type = geo.step_type;
+        if (!Cfg::matches(job->cfg) || !pb::uniform_geometry_of(geo, &ug))
+                return false;
         if (g_specialise == 2)
                 run_tracks_hot(job, Cfg(job->cfg), ug);
         else

@@ -24,6 +24,8 @@ from workloads import WORKLOADS  # noqa: E402
 
 N_TRACKS = {
     "headline": 100000, "rock_3km": 20000, "straight": 100000,
+    "headline_density": 20000, "straight_density": 50000,
+    "csda_density": 100000,
     "straight_mixed": 50000, "csda_water": 200000,
     "csda_spectrum_fwd": 100000, "csda_spectrum_bwd": 100000,
     "csda_limits_fwd": 100000, "csda_limits_bwd": 100000,

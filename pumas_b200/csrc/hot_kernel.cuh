@@ -949,7 +949,8 @@ cudaError_t launch_hot(const Physics & p, const Physics & host_view,
         a.ehs_period = (t.ehs_period > 0) ? t.ehs_period : HOT_EHS_PERIOD;
         a.del_threshold = (t.del_threshold > 0) ? t.del_threshold : 24;
         a.service_patience = (t.service_patience > 0) ? t.service_patience : 3;
-        HotCtx h = hot_context(host_view, p, hotK, hotX, cfg, geo.material);
+        HotCtx h = hot_context(host_view, p, hotK, hotX, cfg, geo.material,
+            geo.density);
 #if PB_HOT_SMEM_TABLES_ON
         h.hotK = HOT_TABLES0;
         h.hotX = HOT_TABLES0 + (unsigned int)(n_cells * HOTK_WORDS);
@@ -1004,13 +1005,9 @@ cudaError_t launch_hot(const Physics & p, const Physics & host_view,
             cudaError_t * error)                                               \
         {                                                                      \
                 typedef StaticSettings<EL, SC, DI, DE> Cfg;                    \
-                if (!Cfg::matches(cfg) ||                                      \
-                    (geo.kind != PUMAS_B200_GEOMETRY_UNIFORM) ||               \
-                    geo.layer[0].has_locals)                                   \
-                        return false;                                          \
                 UniformGeometry ug;                                            \
-                ug.material = geo.layer[0].material;                           \
-                ug.step_type = geo.step_type;                                  \
+                if (!Cfg::matches(cfg) || !uniform_geometry_of(geo, &ug))      \
+                        return false;                                          \
                 *error = launch_hot(p, host_view, p.hotK, p.hotX, Cfg(cfg),    \
                     ug, seed, offset, n, states, events, media, status,        \
                     n_random, n_steps, workspace, stream);                     \

@@ -248,7 +248,7 @@ static cudaError_t launch_csda(const Physics & p, const Physics & host_view,
                     transport_csda_tile_kernel<Cfg>,
                     cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e != cudaSuccess) return e;
-                CsdaCtx c = csda_context(host_view, p, cfg, ug.material);
+                CsdaCtx c = csda_context(host_view, p, cfg, ug.material, ug.density);
                 c.cK = CSDA_TABLES0;
                 c.cX = CSDA_TABLES0 + (unsigned int)(n_cells * CSDAK_WORDS);
                 const int sms = device_sms(current_device());
@@ -281,11 +281,10 @@ bool launch_spec_csda(const Physics & p, const Physics & host_view,
         (void)workspace;
         if ((cfg.energy_loss != MODE_CSDA) ||
             (cfg.scattering != MODE_DISABLED) ||
-            (cfg.decay != MODE_WEIGHTED) || !geometry_is_plain_uniform(geo))
+            (cfg.decay != MODE_WEIGHTED))
                 return false;
         UniformGeometry ug;
-        ug.material = geo.layer[0].material;
-        ug.step_type = geo.step_type;
+        if (!uniform_geometry_of(geo, &ug)) return false;
         BatchArgs a;
         a.seed = seed;
         a.offset = offset;

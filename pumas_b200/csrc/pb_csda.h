@@ -42,7 +42,7 @@ struct CsdaCtx {
  * use (device or host). */
 template <class Cfg>
 inline CsdaCtx csda_context(const Physics & host_view, const Physics & view,
-    const Cfg & cfg, int material)
+    const Cfg & cfg, int material, double density = 0.)
 {
         CsdaCtx c;
         const Physics & p = host_view;
@@ -68,7 +68,7 @@ inline CsdaCtx csda_context(const Physics & host_view, const Physics & view,
         const double * X = col_sm(p, p.X, MODE_CSDA, material);
         c.X0 = X[0];
         c.Xmax = X[nc];
-        c.density = p.material_density[material];
+        c.density = (density > 0.) ? density : p.material_density[material];
         c.mass = p.mass;
         c.ctau = p.ctau;
         c.X_limit_energy = (cfg.event & EVENT_LIMIT_ENERGY) ?

@@ -174,7 +174,8 @@ struct HotCtx {
 
 template <class Cfg>
 inline HotCtx hot_context(const Physics & host_view, const Physics & view,
-    const double * hotK, const double * hotX, const Cfg & cfg, int material)
+    const double * hotK, const double * hotX, const Cfg & cfg, int material,
+    double density = 0.)
 {
         /* `host_view` is read here; `view`, hotK, hotX are the pointers the
          * step will use (device or host). */
@@ -200,7 +201,7 @@ inline HotCtx hot_context(const Physics & host_view, const Physics & view,
         h.Xmax = X[nc];
         h.Ms1_1 = col_Ms1(p, p.Ms1, MODE_MIXED, material)[1];
         h.Lb_1 = col_m(p, p.Lb, material)[1];
-        h.density = p.material_density[material];
+        h.density = (density > 0.) ? density : p.material_density[material];
         h.density_i = 1. / h.density;
         h.mass = p.mass;
         h.ctau = p.ctau;

@@ -115,7 +115,36 @@ PB_FN double set_locals(const Physics & p, const Geometry & g, double accuracy,
 struct UniformGeometry {
         int material;
         int step_type;
+        /* <= 0: the density of the material; else the constant density of a
+         * locals callback without field (examples/pumas/straight.c:61-74 sets
+         * 2.65E+03 that way): transport_set_locals (pumas.c:5528-5552) then
+         * returns that density and no step limit, everything else is the
+         * uniform case. */
+        double density;
 };
+
+/* Is the descriptor a single infinite medium of constant density without
+ * field? Fills `ug`. */
+inline bool uniform_geometry_of(const Geometry & geo, UniformGeometry * ug)
+{
+        if (geo.kind != PUMAS_B200_GEOMETRY_UNIFORM) return false;
+        const struct pumas_b200_layer & l = geo.layer[0];
+        ug->material = l.material;
+        ug->step_type = geo.step_type;
+        ug->density = 0.;
+        if (!l.has_locals) return true;
+        if ((l.density_model != PUMAS_B200_DENSITY_CONSTANT) ||
+            (l.magnet[0] != 0.) || (l.magnet[1] != 0.) || (l.magnet[2] != 0.))
+                return false;
+        ug->density = (l.density > 0.) ? l.density : 0.;
+        return true;
+}
+
+/* The density of the medium. */
+PB_FN double uniform_density(const Physics & p, const UniformGeometry & g)
+{
+        return (g.density > 0.) ? g.density : p.material_density[g.material];
+}
 
 PB_FN int geo_material(const Geometry & g, int medium)
 {
@@ -142,7 +171,7 @@ PB_FN int medium_locate(const UniformGeometry & g, int, const State &,
 PB_FN double set_locals(const Physics & p, const UniformGeometry & g, double,
     int, const State &, Locals * locals)
 {
-        locals->density = p.material_density[g.material];
+        locals->density = uniform_density(p, g);
         locals->magnet[0] = locals->magnet[1] = locals->magnet[2] = 0.;
         locals->magnetized = 0;
         return 0;

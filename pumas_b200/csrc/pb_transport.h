@@ -1121,7 +1121,7 @@ PB_FN void loop_canonical(const Physics & p, const Cfg & cfg,
         lp.step_max_type = g.step_type;
         lp.step_max_medium = 0.;
         lp.step_max_locals = 0.;
-        lp.locals.density = p.material_density[g.material];
+        lp.locals.density = uniform_density(p, g);
         lp.locals.magnet[0] = lp.locals.magnet[1] = lp.locals.magnet[2] = 0.;
         lp.locals.magnetized = 0;
         lp.straight = straight_flag(cfg, 0., lp.locals);

@@ -1529,22 +1529,13 @@ cudaError_t launch_resident(const Physics & p, const Cfg & cfg, const Geo & geo,
             unsigned int * n_random, unsigned int * n_steps, void * workspace, \
             cudaStream_t stream, cudaError_t * error)
 
-/* Is the geometry a single infinite medium without locals callback? */
-inline bool geometry_is_plain_uniform(const Geometry & geo)
-{
-        return (geo.kind == PUMAS_B200_GEOMETRY_UNIFORM) &&
-            !geo.layer[0].has_locals;
-}
-
 #define PB_DEFINE_SPECIALISATION(NAME, EL, SC, DI, DE)                         \
         PB_SPECIALISATION(NAME)                                                \
         {                                                                      \
                 typedef StaticSettings<EL, SC, DI, DE> Cfg;                    \
-                if (!Cfg::matches(cfg) || !geometry_is_plain_uniform(geo))     \
-                        return false;                                          \
                 UniformGeometry ug;                                            \
-                ug.material = geo.layer[0].material;                           \
-                ug.step_type = geo.step_type;                                  \
+                if (!Cfg::matches(cfg) || !uniform_geometry_of(geo, &ug))      \
+                        return false;                                          \
                 *error = launch_resident(p, Cfg(cfg), ug, seed, offset, n,     \
                     states, events, media, status, n_random, n_steps,          \
                     workspace, stream);                                        \

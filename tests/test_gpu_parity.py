@@ -25,6 +25,8 @@ RTOL = 1e-9
 # Tracks per workload (the reference runs them on the host cores in seconds).
 N_TRACKS = {
     "headline": 100000, "rock_3km": 20000, "straight": 100000,
+    "headline_density": 20000, "straight_density": 50000,
+    "csda_density": 100000,
     "straight_mixed": 50000, "csda_water": 200000,
     "csda_spectrum_fwd": 100000, "csda_spectrum_bwd": 100000,
     "csda_limits_fwd": 100000, "csda_limits_bwd": 100000,
@@ -59,6 +61,7 @@ N_TRACKS = {
 DEFAULT_BOUNDS = (0., 0., 1e-9)
 BOUNDS = {
     "headline": (0., 1e-4, 3e-8),
+    "headline_density": (0., 1e-4, 3e-8),
     "rock_3km": (0., 1e-3, 4e-8),
     "limits_all": (0., 2e-4, 1e-7),
     "vertex_stop": (0., 1e-4, 1e-8),

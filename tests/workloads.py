@@ -293,9 +293,25 @@ def dcs_models(material, n, seed=0, direction=MODE_FORWARD,
         states=make_states(n, k, direction=isotropic(n, seed + 1)))
 
 
+def with_density(material, n, seed=0, base=None, density=2.0e3, **kwargs):
+    """A workload of a uniform medium with the density set by a (constant)
+    locals callback, as examples/pumas/straight.c:61-74 does: the fast paths of
+    the uniform medium must apply, with that density."""
+    w = base(material, n, seed=seed, **kwargs)
+    g = w["geometry"]
+    w["geometry"] = uniform_geometry(g.layer[0].material, density=density)
+    return w
+
+
 # name -> (dump, builder, kwargs)
 WORKLOADS = {
     "headline": ("materials.muon", headline, {}),
+    "headline_density": ("materials.muon", with_density,
+                         dict(base=headline, density=3.1e3)),
+    "straight_density": ("materials.muon", with_density,
+                         dict(base=straight, density=2.0e3)),
+    "csda_density": ("materials.muon", with_density,
+                     dict(base=csda_water, density=0.92e3)),
     "straight": ("materials.muon", straight, {}),
     "straight_mixed": ("materials.muon", straight,
                        dict(scattering=MODE_MIXED, spectrum=True)),
